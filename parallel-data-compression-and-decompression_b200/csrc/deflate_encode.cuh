@@ -1,0 +1,555 @@
+// deflate_encode.cuh — parse + dynamic Huffman + bit packing, one warp per chunk.
+//
+// Second half of the replacement for zlib's deflate() at compression.cpp:119-134. Input: the per-position best matches
+// left in HBM scratch by lz_match_kernel and the raw chunk. Output: one complete zlib stream (78 9C, one final DEFLATE
+// block — stored, fixed or dynamic, whichever is smallest — and the big-endian Adler-32), or two stored streams when
+// even the smallest encoding would not fit the reader's 65 535-byte payload array (decompression.cpp:116).
+//
+// Per warp:
+//   parse   32 positions per step. Every lane decides locally "match here or literal" with zlib-style lazy evaluation
+//           (a match is deferred when the next position has a longer one), which makes `next[i]` a pure function of the
+//           scratch; the token path through the window is then recovered with 5 rounds of pointer doubling on
+//           (jump, reach-mask) pairs exchanged by warp shuffles; tokens are compacted in place with ballot + popc and
+//           the literal/length and distance histograms are updated with shared-memory atomics.
+//   codes   symbols ranked by frequency (rank sort across lanes), two-queue Huffman merge, depth histogram clamped to
+//           15 (7 for the code-length alphabet) with zlib's overflow repair, lengths re-assigned by rank, canonical codes
+//           assigned 32 symbols per step with __match_any_sync, bit-reversed for LSB-first output.
+//   header  code lengths run-length coded exactly like RFC 1951 §3.2.7 allows (16/17/18), third Huffman code over that.
+//   emit    32 tokens per step: each lane builds its <= 48-bit code, a warp-shuffle inclusive prefix sum of the bit counts
+//           gives every lane its bit offset, lanes OR their bits into a shared-memory staging window and full 32-bit words
+//           are flushed to the output slot with one coalesced store.
+//
+// Algorithmic HBM bytes per chunk: N_raw read + N_comp written; the scratch round trip (8 N_raw) is
+// design traffic.
+#pragma once
+#include "zwz_common.cuh"
+
+namespace zwz {
+
+#define ZWZ_DE_WARPS 4
+#define ZWZ_DE_LL 286
+#define ZWZ_DE_D 30
+#define ZWZ_DE_DOFF 288 // distance symbols live at freq[288 + d]
+
+struct EncWarpSmem {
+    uint32_t freq[320];     // [0,286) literal/length, [288,318) distance
+    uint32_t code[320];     // (bit length << 16) | bit-reversed code
+    uint32_t clfreq[20];    // code-length alphabet
+    uint32_t clcode[20];
+    uint32_t key[288];      // (freq << 9 | symbol) of used symbols, then sorted ascending
+    uint32_t weight[576];   // leaves then internal nodes
+    uint16_t parent[576];
+    uint8_t blen[320];      // code lengths (literal/length at 0, distance at 288)
+    uint8_t clblen[20];
+    uint32_t bl_count[16];
+    uint32_t next_code[16];
+    uint8_t cl_sym[320];    // run-length coded code lengths
+    uint8_t cl_ext[320];
+    uint32_t stage[64];     // bit sink staging window
+    uint32_t misc[8];
+};
+
+// -------------------------------------------------------------------------------------------------------------------
+// Length-limited Huffman code for the `nsym` symbols whose counts are freq[0..nsym). Writes blen[] and code[].
+// -------------------------------------------------------------------------------------------------------------------
+ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, uint32_t maxbits, uint8_t *blen, uint32_t *code) {
+    const unsigned lane = lane_id();
+    // 1. compact used symbols into keys
+    uint32_t nused = 0;
+    for (uint32_t base = 0; base < nsym; base += 32u) {
+        uint32_t s = base + lane;
+        uint32_t f = s < nsym ? freq[s] : 0u;
+        unsigned m = __ballot_sync(ZWZ_FULL, f != 0u);
+        if (f) S.key[nused + (uint32_t) __popc(m & ((1u << lane) - 1u))] = (f << 9) | s;
+        nused += (uint32_t) __popc(m);
+        if (s < nsym) blen[s] = 0;
+    }
+    __syncwarp();
+    // zlib's rule (trees.c build_tree): force at least two codes so the code is complete and every decoder accepts it
+    if (nused < 2u) {
+        if (lane == 0) {
+            uint32_t have = nused ? (S.key[0] & 511u) : 0xffffu;
+            uint32_t d0 = have == 0u ? 1u : 0u;
+            S.key[nused] = (1u << 9) | d0;
+            if (nused == 0u) S.key[1] = (1u << 9) | 1u;
+        }
+        nused = 2u;
+        __syncwarp();
+    }
+    // 2. rank sort ascending by (freq, symbol) into weight[]/sorted order; keys are unique
+    uint32_t mykey[9], myrank[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        uint32_t i = lane + 32u * k;
+        mykey[k] = i < nused ? S.key[i] : 0xffffffffu;
+        myrank[k] = 0;
+    }
+    for (uint32_t j = 0; j < nused; ++j) {
+        uint32_t kj = S.key[j];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) myrank[k] += kj < mykey[k] ? 1u : 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        uint32_t i = lane + 32u * k;
+        if (i < nused) S.key[myrank[k]] = mykey[k];
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nused; i += 32u) S.weight[i] = S.key[i] >> 9;
+    __syncwarp();
+    // 3. two-queue merge (serial; the data is tiny and sorted, the other lanes wait)
+    if (lane == 0) {
+        uint32_t leaf = 0, inode = nused, next = nused;
+        const uint32_t last = 2u * nused - 1u;
+        while (next < last) {
+            uint32_t pick[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                bool take_leaf = leaf < nused && (inode >= next || S.weight[leaf] <= S.weight[inode]);
+                pick[t] = take_leaf ? leaf++ : inode++;
+            }
+            S.weight[next] = S.weight[pick[0]] + S.weight[pick[1]];
+            S.parent[pick[0]] = (uint16_t) next;
+            S.parent[pick[1]] = (uint16_t) next;
+            ++next;
+        }
+        S.parent[last - 1u] = 0xffffu; // root
+    }
+    if (lane < 16u) S.bl_count[lane] = 0;
+    __syncwarp();
+    // 4. leaf depths (walk to the root), histogram clamped at maxbits
+    const uint32_t root = 2u * nused - 2u;
+    uint32_t overflow = 0;
+    for (uint32_t i = lane; i < nused; i += 32u) {
+        uint32_t d = 0, v = i;
+        while (v != root) {
+            v = S.parent[v];
+            ++d;
+        }
+        if (d > maxbits) {
+            d = maxbits;
+            ++overflow;
+        }
+        atomicAdd(&S.bl_count[d], 1u);
+    }
+    overflow = warp_sum(overflow);
+    __syncwarp();
+    // 5. zlib gen_bitlen repair: move leaves up until the Kraft sum fits
+    if (overflow && lane == 0) {
+        int ov = (int) overflow;
+        do {
+            uint32_t bits = maxbits - 1u;
+            while (S.bl_count[bits] == 0u) --bits;
+            S.bl_count[bits]--;
+            S.bl_count[bits + 1u] += 2u;
+            S.bl_count[maxbits]--;
+            ov -= 2;
+        } while (ov > 0);
+    }
+    __syncwarp();
+    // 6. lengths by rank: the rarest symbols take the longest codes
+    {
+        uint32_t cum[16];
+        uint32_t acc = 0;
+#pragma unroll
+        for (int b = 15; b >= 1; --b) {
+            acc += (uint32_t) b <= maxbits ? S.bl_count[b] : 0u;
+            cum[b] = acc; // symbols with rank < cum[b] have length >= b
+        }
+        for (uint32_t i = lane; i < nused; i += 32u) {
+            uint32_t L = 1;
+#pragma unroll
+            for (int b = 2; b <= 15; ++b)
+                if (i < cum[b]) L = (uint32_t) b;
+            blen[S.key[i] & 511u] = (uint8_t) L;
+        }
+    }
+    // 7. canonical codes
+    if (lane == 0) {
+        uint32_t c = 0;
+        S.next_code[0] = 0;
+        for (uint32_t b = 1; b <= 15u; ++b) {
+            c = (c + (b - 1u <= maxbits && b > 1u ? S.bl_count[b - 1u] : 0u)) << 1;
+            S.next_code[b] = c;
+        }
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < nsym; base += 32u) {
+        uint32_t s = base + lane;
+        uint32_t L = s < nsym ? blen[s] : 0u;
+        unsigned grp = __match_any_sync(ZWZ_FULL, L);
+        if (s < nsym) {
+            uint32_t cw = 0;
+            if (L) {
+                cw = S.next_code[L] + (uint32_t) __popc(grp & ((1u << lane) - 1u));
+                cw = __brev(cw) >> (32u - L);
+            }
+            code[s] = (L << 16) | cw;
+        }
+        __syncwarp();
+        if (L && (grp >> lane) == 1u) S.next_code[L] += (uint32_t) __popc(grp);
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// bit sink: warp-collective append of (bits, nbits <= 57) per lane, in lane order
+// -------------------------------------------------------------------------------------------------------------------
+struct BitSink {
+    uint32_t *outw;    // 4-byte aligned output words
+    uint32_t nwords;   // words already stored
+    uint32_t fill;     // bits waiting in stage[0]
+};
+
+ZWZ_DEV void sink_init(EncWarpSmem &S, BitSink &k, uint32_t *outw) {
+    k.outw = outw;
+    k.nwords = 0;
+    k.fill = 0;
+    S.stage[lane_id()] = 0;
+    S.stage[lane_id() + 32u] = 0;
+    __syncwarp();
+}
+ZWZ_DEV void sink_put(EncWarpSmem &S, BitSink &k, uint64_t bits, uint32_t nbits) {
+    const unsigned lane = lane_id();
+    uint32_t incl = warp_incl_scan(nbits);
+    uint32_t total = __shfl_sync(ZWZ_FULL, incl, 31);
+    if (nbits) {
+        uint32_t pos = k.fill + incl - nbits;
+        uint32_t w = pos >> 5, sh = pos & 31u;
+        uint64_t lo = bits << sh;
+        uint32_t hi = sh ? (uint32_t) (bits >> (64u - sh)) : 0u;
+        atomicOr(&S.stage[w], (uint32_t) lo);
+        if ((uint32_t) (lo >> 32)) atomicOr(&S.stage[w + 1u], (uint32_t) (lo >> 32));
+        if (hi) atomicOr(&S.stage[w + 2u], hi);
+    }
+    __syncwarp();
+    uint32_t nf = k.fill + total;
+    uint32_t full = nf >> 5;
+    uint32_t v0 = S.stage[lane], v1 = S.stage[lane + 32u];
+    if (lane < full) k.outw[k.nwords + lane] = v0;
+    if (lane + 32u < full) k.outw[k.nwords + lane + 32u] = v1;
+    uint32_t carry = __shfl_sync(ZWZ_FULL, full < 32u ? v0 : v1, (int) (full & 31u));
+    __syncwarp();
+    S.stage[lane] = lane == 0 ? carry : 0u;
+    S.stage[lane + 32u] = 0;
+    __syncwarp();
+    k.nwords += full;
+    k.fill = nf & 31u;
+}
+// store the partial last word; returns total bytes
+ZWZ_DEV uint32_t sink_finish(EncWarpSmem &S, BitSink &k) {
+    if (k.fill && lane_id() == 0) k.outw[k.nwords] = S.stage[0];
+    return k.nwords * 4u + ((k.fill + 7u) >> 3);
+}
+
+ZWZ_DEV uint32_t enc_adler_global(const uint8_t *p, uint32_t n) {
+    uint64_t s0 = 0, s1 = 0;
+    for (uint32_t j = lane_id(); j < n; j += 32u) {
+        uint32_t v = p[j];
+        s0 += v;
+        s1 += (uint64_t) j * v;
+    }
+    s0 = warp_sum64(s0) % 65521u;
+    s1 = warp_sum64(s1 % 65521u) % 65521u;
+    uint64_t nm = n % 65521u;
+    uint32_t a = (uint32_t) ((1u + s0) % 65521u);
+    uint32_t b = (uint32_t) ((nm + nm * s0 + 65521u - s1) % 65521u);
+    return (b << 16) | a;
+}
+
+// one complete zlib stream with a single stored block; returns its size
+ZWZ_DEV uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, uint32_t n, uint32_t adler) {
+    const unsigned lane = lane_id();
+    if (lane == 0) {
+        out[0] = 0x78;
+        out[1] = 0x9c;
+        out[2] = 0x01;
+        out[3] = (uint8_t) n;
+        out[4] = (uint8_t) (n >> 8);
+        out[5] = (uint8_t) ~n;
+        out[6] = (uint8_t) (~n >> 8);
+        out[7 + n] = (uint8_t) (adler >> 24);
+        out[8 + n] = (uint8_t) (adler >> 16);
+        out[9 + n] = (uint8_t) (adler >> 8);
+        out[10 + n] = (uint8_t) adler;
+    }
+    for (uint32_t i = lane; i < n; i += 32u) out[7u + i] = src[i];
+    return n + 11u;
+}
+
+ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
+    const unsigned lane = lane_id();
+    const uint32_t n = job.raw_len[c];
+    const uint8_t *src = job.raw + job.raw_off[c];
+    uint32_t *m = job.scratch + job.scr_off[c];
+    uint8_t *out = job.out + job.out_off[c];
+
+    for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] = 0;
+    __syncwarp();
+
+    // ---------------- parse ----------------
+    uint32_t ntok = 0;
+    uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)
+    for (uint32_t p = 0; p < n;) {
+        uint32_t q = p + lane;
+        uint32_t m0 = q < n ? m[q] : 0u;
+        uint32_t m1 = __shfl_down_sync(ZWZ_FULL, m0, 1);
+        uint32_t mnext = (lane == 31u && q + 1u < n) ? m[q + 1u] : 0u;
+        if (lane == 31u) m1 = mnext;
+        uint32_t len0 = m0 >> 16, len1 = m1 >> 16;
+        bool take = len0 >= ZWZ_MIN_MATCH && !(len1 > len0);
+        uint32_t J = lane + (take ? len0 : 1u);
+        uint32_t R = 1u << lane;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            int from = J < 32u ? (int) J : (int) lane;
+            uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);
+            uint32_t Jj = __shfl_sync(ZWZ_FULL, J, from);
+            if (J < 32u) {
+                R |= Rj;
+                J = Jj;
+            }
+        }
+        uint32_t R0 = __shfl_sync(ZWZ_FULL, R, 0);
+        uint32_t J0 = __shfl_sync(ZWZ_FULL, J, 0);
+        bool marked = ((R0 >> lane) & 1u) && q < n;
+        unsigned tm = __ballot_sync(ZWZ_FULL, marked);
+        if (marked) {
+            uint32_t tok;
+            if (take) {
+                tok = m0;
+                uint32_t ls, le, lv, ds, de, dv;
+                len_symbol(len0, ls, le, lv);
+                dist_symbol(m0 & 0xffffu ? (m0 & 0xffffu) : 65536u, ds, de, dv);
+                atomicAdd(&S.freq[ls], 1u);
+                atomicAdd(&S.freq[ZWZ_DE_DOFF + ds], 1u);
+                extra_bits += le + de;
+            } else {
+                tok = src[q];
+                atomicAdd(&S.freq[tok], 1u);
+            }
+            m[ntok + (uint32_t) __popc(tm & ((1u << lane) - 1u))] = tok;
+        }
+        ntok += (uint32_t) __popc(tm);
+        p += J0;
+    }
+    if (lane == 0) S.freq[256] += 1u; // end of block
+    extra_bits = warp_sum64(extra_bits);
+    __syncwarp();
+
+    // ---------------- codes ----------------
+    enc_huffman(S, S.freq, ZWZ_DE_LL, 15u, S.blen, S.code);
+    enc_huffman(S, S.freq + ZWZ_DE_DOFF, ZWZ_DE_D, 15u, S.blen + ZWZ_DE_DOFF, S.code + ZWZ_DE_DOFF);
+    __syncwarp();
+
+    // HLIT / HDIST: highest used symbol + 1
+    uint32_t hl = 0, hd = 0;
+    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u)
+        if (S.blen[s]) hl = s + 1u;
+    if (lane < ZWZ_DE_D && S.blen[ZWZ_DE_DOFF + lane]) hd = lane + 1u;
+    hl = warp_max(hl);
+    hd = warp_max(hd);
+    if (hl < 257u) hl = 257u;
+    if (hd < 1u) hd = 1u;
+
+    // ---------------- code-length run-length coding (RFC 1951 §3.2.7; same run rules as zlib's scan_tree) ----------------
+    if (lane < 20u) S.clfreq[lane] = 0;
+    __syncwarp();
+    uint32_t ncl = 0;
+    if (lane == 0) {
+        for (int part = 0; part < 2; ++part) {
+            const uint8_t *L = part == 0 ? S.blen : S.blen + ZWZ_DE_DOFF;
+            uint32_t cnt_syms = part == 0 ? hl : hd;
+            int prevlen = -1;
+            uint32_t i = 0;
+            while (i < cnt_syms) {
+                uint32_t cur = L[i];
+                uint32_t run = 1;
+                uint32_t maxrun = cur == 0u ? 138u : ((int) cur == prevlen ? 6u : 7u);
+                while (i + run < cnt_syms && L[i + run] == cur && run < maxrun) ++run;
+                uint32_t minrun = cur == 0u ? 3u : ((int) cur == prevlen ? 3u : 4u);
+                if (run < minrun) {
+                    for (uint32_t r = 0; r < run; ++r) {
+                        S.cl_sym[ncl] = (uint8_t) cur;
+                        S.cl_ext[ncl++] = 0;
+                    }
+                    S.clfreq[cur] += run;
+                } else if (cur != 0u) {
+                    uint32_t rep = run;
+                    if ((int) cur != prevlen) {
+                        S.cl_sym[ncl] = (uint8_t) cur;
+                        S.cl_ext[ncl++] = 0;
+                        S.clfreq[cur] += 1u;
+                        rep = run - 1u;
+                    }
+                    S.cl_sym[ncl] = 16;
+                    S.cl_ext[ncl++] = (uint8_t) (rep - 3u);
+                    S.clfreq[16] += 1u;
+                } else if (run <= 10u) {
+                    S.cl_sym[ncl] = 17;
+                    S.cl_ext[ncl++] = (uint8_t) (run - 3u);
+                    S.clfreq[17] += 1u;
+                } else {
+                    S.cl_sym[ncl] = 18;
+                    S.cl_ext[ncl++] = (uint8_t) (run - 11u);
+                    S.clfreq[18] += 1u;
+                }
+                prevlen = (int) cur;
+                i += run;
+            }
+        }
+        S.misc[0] = ncl;
+    }
+    __syncwarp();
+    ncl = S.misc[0];
+    enc_huffman(S, S.clfreq, 19u, 7u, S.clblen, S.clcode);
+    __syncwarp();
+    // HCLEN: last used entry in the transmission order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+    uint32_t ord = lane < 3u ? 16u + lane : (lane == 3u ? 0u : ((lane & 1u) ? 7u - ((lane - 5u) >> 1) : 8u + ((lane - 4u) >> 1)));
+    uint32_t hc = (lane < 19u && S.clblen[ord]) ? lane + 1u : 0u;
+    hc = warp_max(hc);
+    if (hc < 4u) hc = 4u;
+
+    // ---------------- sizes ----------------
+    uint64_t dyn_bits = 0, fix_bits = 0, hdr_bits = 0;
+    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u) {
+        uint32_t f = S.freq[s];
+        dyn_bits += (uint64_t) f * S.blen[s];
+        fix_bits += (uint64_t) f * (s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u)));
+    }
+    if (lane < ZWZ_DE_D) {
+        uint32_t f = S.freq[ZWZ_DE_DOFF + lane];
+        dyn_bits += (uint64_t) f * S.blen[ZWZ_DE_DOFF + lane];
+        fix_bits += (uint64_t) f * 5u;
+    }
+    if (lane < 19u) hdr_bits += (uint64_t) S.clfreq[lane] * (S.clblen[lane] + (lane == 16u ? 2u : (lane == 17u ? 3u : (lane == 18u ? 7u : 0u))));
+    dyn_bits = warp_sum64(dyn_bits) + extra_bits;
+    fix_bits = warp_sum64(fix_bits) + extra_bits;
+    hdr_bits = warp_sum64(hdr_bits) + 14u + 3u * hc;
+    const uint64_t dyn_total = 3u + hdr_bits + dyn_bits;
+    const uint64_t fix_total = 3u + fix_bits;
+    const uint32_t dyn_bytes = (uint32_t) ((dyn_total + 7u) >> 3) + 6u;
+    const uint32_t fix_bytes = (uint32_t) ((fix_total + 7u) >> 3) + 6u;
+    const uint32_t sto_bytes = n + 11u;
+    uint32_t btype = 2u, best = dyn_bytes;
+    if (fix_bytes <= best) {
+        btype = 1u;
+        best = fix_bytes;
+    }
+    if (sto_bytes < best) {
+        btype = 0u;
+        best = sto_bytes;
+    }
+
+    uint32_t len0 = 0, len1 = 0, raw0 = n;
+    const uint32_t adler = job.adler[c];
+    if (best > ZWZ_CHUNK) {
+        // split rule: two stored streams over the halves (each needs its own Adler-32)
+        raw0 = 32768u;
+        uint32_t a0 = enc_adler_global(src, raw0);
+        uint32_t a1 = enc_adler_global(src + raw0, n - raw0);
+        len0 = enc_stored_stream(out, src, raw0, a0);
+        len1 = enc_stored_stream(out + len0, src + raw0, n - raw0, a1);
+        btype = 0u;
+    } else if (btype == 0u) {
+        len0 = enc_stored_stream(out, src, n, adler);
+    } else {
+        BitSink k;
+        sink_init(S, k, (uint32_t *) out);
+        if (btype == 1u) {
+            // fixed codes (RFC 1951 §3.2.6) into the same code[] layout
+            for (uint32_t s = lane; s < 288u; s += 32u) {
+                uint32_t L = s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u));
+                uint32_t cw = s < 144u ? 0x30u + s : (s < 256u ? 0x190u + (s - 144u) : (s < 280u ? s - 256u : 0xC0u + (s - 280u)));
+                if (s < ZWZ_DE_LL) S.code[s] = (L << 16) | (__brev(cw) >> (32u - L));
+            }
+            if (lane < ZWZ_DE_D) S.code[ZWZ_DE_DOFF + lane] = (5u << 16) | (__brev(lane) >> 27);
+            __syncwarp();
+            sink_put(S, k, lane == 0 ? (0x9c78ull | (3ull << 16)) : 0ull, lane == 0 ? 19u : 0u);
+        } else {
+            // 78 9C, BFINAL=1 BTYPE=10, HLIT, HDIST, HCLEN, then HCLEN 3-bit lengths (lanes 1..19)
+            uint64_t v = 0;
+            uint32_t nb = 0;
+            if (lane == 0) {
+                v = 0x9c78ull | (5ull << 16) | ((uint64_t) (hl - 257u) << 19) | ((uint64_t) (hd - 1u) << 24) | ((uint64_t) (hc - 4u) << 29);
+                nb = 33u;
+            } else if (lane <= hc) {
+                uint32_t o = lane - 1u;
+                uint32_t od = o < 3u ? 16u + o : (o == 3u ? 0u : ((o & 1u) ? 7u - ((o - 5u) >> 1) : 8u + ((o - 4u) >> 1)));
+                v = S.clblen[od];
+                nb = 3u;
+            }
+            sink_put(S, k, v, nb);
+            for (uint32_t base = 0; base < ncl; base += 32u) {
+                uint32_t i = base + lane;
+                uint64_t b = 0;
+                uint32_t nbits = 0;
+                if (i < ncl) {
+                    uint32_t sy = S.cl_sym[i];
+                    uint32_t cw = S.clcode[sy];
+                    nbits = cw >> 16;
+                    b = cw & 0xffffu;
+                    uint32_t eb = sy == 16u ? 2u : (sy == 17u ? 3u : (sy == 18u ? 7u : 0u));
+                    b |= (uint64_t) S.cl_ext[i] << nbits;
+                    nbits += eb;
+                }
+                sink_put(S, k, b, nbits);
+            }
+        }
+        // tokens, then end-of-block
+        for (uint32_t base = 0; base <= ntok; base += 32u) {
+            uint32_t i = base + lane;
+            uint64_t b = 0;
+            uint32_t nbits = 0;
+            if (i < ntok) {
+                uint32_t tok = m[i];
+                uint32_t len = tok >> 16;
+                if (len == 0u) {
+                    uint32_t cw = S.code[tok];
+                    nbits = cw >> 16;
+                    b = cw & 0xffffu;
+                } else {
+                    uint32_t dist = tok & 0xffffu ? (tok & 0xffffu) : 65536u;
+                    uint32_t ls, le, lv, ds, de, dv;
+                    len_symbol(len, ls, le, lv);
+                    dist_symbol(dist, ds, de, dv);
+                    uint32_t cl = S.code[ls], cd = S.code[ZWZ_DE_DOFF + ds];
+                    b = cl & 0xffffu;
+                    nbits = cl >> 16;
+                    b |= (uint64_t) lv << nbits;
+                    nbits += le;
+                    b |= (uint64_t) (cd & 0xffffu) << nbits;
+                    nbits += cd >> 16;
+                    b |= (uint64_t) dv << nbits;
+                    nbits += de;
+                }
+            } else if (i == ntok) {
+                uint32_t cw = S.code[256];
+                nbits = cw >> 16;
+                b = cw & 0xffffu;
+            }
+            sink_put(S, k, b, nbits);
+        }
+        // pad to a byte boundary, Adler-32 big-endian
+        uint32_t padbits = (8u - ((k.nwords * 32u + k.fill) & 7u)) & 7u;
+        uint32_t be = ((adler & 0xffu) << 24) | ((adler & 0xff00u) << 8) | ((adler >> 8) & 0xff00u) | (adler >> 24);
+        sink_put(S, k, lane == 1u ? (uint64_t) be : 0ull, lane == 0 ? padbits : (lane == 1u ? 32u : 0u));
+        len0 = sink_finish(S, k);
+    }
+    if (lane == 0) {
+        job.res[4u * c + 0u] = len0;
+        job.res[4u * c + 1u] = len1;
+        job.res[4u * c + 2u] = raw0;
+        job.res[4u * c + 3u] = btype;
+    }
+}
+
+ZWZ_KERNEL __launch_bounds__(ZWZ_DE_WARPS * 32) deflate_encode_kernel(DeflateJob job) {
+    __shared__ EncWarpSmem smem[ZWZ_DE_WARPS];
+    uint32_t c = blockIdx.x * ZWZ_DE_WARPS + warp_id();
+    if (c >= job.n) return;
+    enc_chunk(smem[warp_id()], job, c);
+}
+
+} // namespace zwz

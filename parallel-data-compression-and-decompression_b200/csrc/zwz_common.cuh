@@ -1,0 +1,137 @@
+// zwz_common.cuh — shared device-side helpers for the sm_100a kernels.
+//
+// Every kernel source in this directory compiles two ways:
+//   nvcc -gencode arch=compute_100a,code=sm_100a            -> the product (libzwz_cuda.so)
+//   g++  -DZWZ_EMU -include tests/simt/simt_emu.h           -> the CPU SIMT emulator build used ONLY by tests
+// so the few places that need inline PTX (bulk async copy + mbarrier) have a plain-loop twin under ZWZ_EMU.
+#pragma once
+#include <stdint.h>
+#include "zwz_cuda.h"
+
+#ifdef ZWZ_EMU
+#define ZWZ_DEV static inline
+#define ZWZ_KERNEL static void
+#define ZWZ_DYN_SMEM(name) unsigned char *name = simt::dyn_smem()
+#define ZWZ_SPIN_PAUSE() zwz_emu_spin_pause()
+#else
+#include <cuda_runtime.h>
+#define ZWZ_DEV __device__ __forceinline__
+#define ZWZ_KERNEL __global__ void
+#define ZWZ_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define ZWZ_SPIN_PAUSE() __nanosleep(20)
+#endif
+
+#define ZWZ_FULL 0xffffffffu
+#define ZWZ_CHUNK 65535u
+#define ZWZ_MIN_MATCH 3u
+#define ZWZ_MAX_MATCH 258u
+#define ZWZ_MAX_DIST 32768u
+
+namespace zwz {
+
+ZWZ_DEV unsigned lane_id() { return threadIdx.x & 31u; }
+ZWZ_DEV unsigned warp_id() { return threadIdx.x >> 5; }
+
+// chunk descriptor / result as laid out in device memory (structure of arrays, one entry per chunk)
+struct DeflateJob {
+    const uint8_t *raw;        // all chunks' raw bytes
+    const uint64_t *raw_off;   // [n]
+    const uint32_t *raw_len;   // [n]   <= 65535
+    const uint64_t *scr_off;   // [n]   offset (in uint32 units) of this chunk's match/token scratch
+    uint32_t *scratch;         // 4 bytes per raw byte (+ pad)
+    uint32_t *adler;           // [n]   written by the match kernel, read by the encoder
+    uint8_t *out;              // output slots
+    const uint64_t *out_off;   // [n]   multiple of 4, capacity >= zwz_deflate_bound(len)
+    uint32_t *res;             // [n*4] zwz_deflate_result
+    uint32_t n;
+    uint32_t depth;            // hash-chain candidates examined per position
+    uint32_t nice;             // stop searching at this length
+    uint32_t *work_counter;    // persistent-CTA work queue
+};
+
+// ---- unaligned little-endian loads built from aligned 32-bit words -------------------------------------------------
+// `w` is a 4-byte-aligned array, `i` a byte index into it. Reads the two words covering bytes [i, i+4).
+ZWZ_DEV uint32_t ld32u(const uint32_t *w, uint32_t i) {
+    uint32_t k = i >> 2;
+    uint32_t lo = w[k], hi = w[k + 1];
+    return __funnelshift_r(lo, hi, (i & 3u) * 8u);
+}
+
+ZWZ_DEV uint32_t warp_incl_scan(uint32_t v) {
+    unsigned l = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(ZWZ_FULL, v, d);
+        if (l >= (unsigned) d) v += t;
+    }
+    return v;
+}
+ZWZ_DEV uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ZWZ_FULL, v, d);
+    return v;
+}
+ZWZ_DEV uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ZWZ_FULL, v, d);
+    return v;
+}
+ZWZ_DEV uint32_t warp_max(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uint32_t t = __shfl_xor_sync(ZWZ_FULL, v, d);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// ---- DEFLATE symbol arithmetic (RFC 1951 §3.2.5) without tables ----------------------------------------------------
+// length 3..258 -> (symbol 257..285, extra bit count, extra value)
+ZWZ_DEV void len_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
+    uint32_t l = len - 3u;
+    if (l < 8u) {
+        sym = 257u + l;
+        ebits = 0;
+        eval = 0;
+    } else if (len == 258u) {
+        sym = 285u;
+        ebits = 0;
+        eval = 0;
+    } else {
+        uint32_t nb = 31u - (uint32_t) __clz((int) l); // >= 3
+        sym = 257u + 4u * (nb - 1u) + ((l >> (nb - 2u)) & 3u);
+        ebits = nb - 2u;
+        eval = l & ((1u << ebits) - 1u);
+    }
+}
+// distance 1..32768 -> (symbol 0..29, extra bit count, extra value)
+ZWZ_DEV void dist_symbol(uint32_t dist, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
+    uint32_t d = dist - 1u;
+    if (d < 4u) {
+        sym = d;
+        ebits = 0;
+        eval = 0;
+    } else {
+        uint32_t nb = 31u - (uint32_t) __clz((int) d); // >= 2
+        sym = 2u * nb + ((d >> (nb - 1u)) & 1u);
+        ebits = nb - 1u;
+        eval = d & ((1u << ebits) - 1u);
+    }
+}
+
+// Adler-32 partial sums over a byte range handled by one thread, to be combined with adler_combine.
+struct AdlerPart {
+    uint32_t a; // sum of bytes            (mod 65521)
+    uint32_t b; // sum of (len - j) * byte (mod 65521)
+    uint32_t len;
+};
+// (A then B) as one range: a = aA + aB ; b = bA + bB + lenB * aA
+ZWZ_DEV AdlerPart adler_combine(const AdlerPart &x, const AdlerPart &y) {
+    AdlerPart r;
+    r.a = (x.a + y.a) % 65521u;
+    r.b = (uint32_t) (((uint64_t) x.b + y.b + (uint64_t) (y.len % 65521u) * x.a) % 65521u);
+    r.len = x.len + y.len;
+    return r;
+}
+
+} // namespace zwz

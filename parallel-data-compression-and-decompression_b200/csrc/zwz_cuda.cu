@@ -1,0 +1,549 @@
+// zwz_cuda.cu — implementation of the C ABI in include/zwz_cuda.h over the sm_100a kernels in this directory.
+//
+// One zwz_ctx per GPU: a non-blocking stream, grow-only device arenas (chunk descriptors, match/token scratch, bulk
+// staging for the host-buffer entry points) and a pinned arena for descriptors/results. No CPU fallback: every entry
+// point either runs the CUDA kernels or returns an error.
+#include "zwz_cuda.h"
+#include "zwz_rt.h"
+
+#include "zwz_common.cuh"
+#include "md5.cuh"
+#include "inflate.cuh"
+#include "deflate_match.cuh"
+#include "deflate_encode.cuh"
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+namespace zwz {
+
+// warp-per-chunk gather of the variable-length streams out of their slots into one packed buffer
+ZWZ_KERNEL pack_streams_kernel(const uint8_t *__restrict__ slots, const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ res,
+                               uint8_t *packed, const uint64_t *__restrict__ packed_off, uint32_t n) {
+    uint32_t c = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (c >= n) return;
+    const uint8_t *s = slots + slot_off[c];
+    uint8_t *d = packed + packed_off[c];
+    uint32_t bytes = res[4u * c] + res[4u * c + 1u];
+    unsigned lane = lane_id();
+    // slots are 4-byte aligned; use word copies when the destination happens to be too
+    if ((((uintptr_t) d) & 3u) == 0u) {
+        uint32_t nw = bytes >> 2;
+        for (uint32_t i = lane; i < nw; i += 32u) ((uint32_t *) d)[i] = ((const uint32_t *) s)[i];
+        for (uint32_t i = (nw << 2) + lane; i < bytes; i += 32u) d[i] = s[i];
+    } else {
+        for (uint32_t i = lane; i < bytes; i += 32u) d[i] = s[i];
+    }
+}
+
+// Adler-32 of arbitrary ranges, one warp each (exported for tests; the deflate path fuses it into lz_match_kernel)
+ZWZ_KERNEL adler32_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
+                          uint32_t *adler, uint32_t n) {
+    uint32_t c = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (c >= n) return;
+    uint32_t a = enc_adler_global(data + off[c], len[c]);
+    if (lane_id() == 0) adler[c] = a;
+}
+
+struct Arena {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+};
+
+} // namespace zwz
+
+struct zwz_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0, smem_optin = 0;
+    zwz_stream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, counter;
+    size_t batch_raw_bytes = (size_t) 1 << 30; // raw bytes per internal deflate sub-batch (scratch = 4x that)
+};
+
+namespace {
+
+using zwz::Arena;
+
+int fail(zwz_ctx *ctx, int code, const char *what) {
+    if (ctx) {
+        std::string cuda;
+        zwz_rt::last_error(cuda);
+        ctx->err = what;
+        if (!cuda.empty()) ctx->err += std::string(": ") + cuda;
+    }
+    return code;
+}
+
+int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
+    if (a.cap >= bytes && a.p) return ZWZ_OK;
+    if (a.p) {
+        zwz_rt::stream_sync(ctx->stream);
+        if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_device(a.p);
+        a.p = nullptr;
+        a.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096; // grow-only, with headroom
+    int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : zwz_rt::malloc_device(&a.p, want);
+    if (rc) {
+        a.p = nullptr;
+        return fail(ctx, ZWZ_E_NOMEM, pinned ? "pinned allocation failed" : "device allocation failed");
+    }
+    a.cap = want;
+    a.pinned = pinned;
+    return ZWZ_OK;
+}
+
+void release(Arena &a) {
+    if (!a.p) return;
+    if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_device(a.p);
+    a.p = nullptr;
+    a.cap = 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_launch(zwz_ctx *ctx, const char *what) {
+    ctx->launches++;
+    std::string msg;
+    if (zwz_rt::last_error(msg)) {
+        ctx->err = std::string(what) + ": " + msg;
+        return ZWZ_E_CUDA;
+    }
+    return ZWZ_OK;
+}
+
+struct LevelParams {
+    uint32_t depth, nice;
+};
+LevelParams level_params(int level) {
+    // search effort per level; 0 = default (6)
+    static const LevelParams t[10] = {{32, 128}, {4, 16}, {6, 24}, {8, 32}, {16, 64}, {24, 96}, {32, 128}, {64, 160}, {128, 258}, {512, 258}};
+    if (level < 0 || level > 9) level = 0;
+    return t[level];
+}
+
+} // namespace
+
+extern "C" {
+
+int zwz_abi_version(void) { return ZWZ_ABI_VERSION; }
+int zwz_device_count(void) { return zwz_rt::device_count(); }
+
+int zwz_init(int device, zwz_ctx **out) {
+    if (!out) return ZWZ_E_ARG;
+    *out = nullptr;
+    if (device < 0 || device >= zwz_rt::device_count()) return ZWZ_E_NODEVICE;
+    if (zwz_rt::set_device(device)) return ZWZ_E_NODEVICE;
+    zwz_ctx *ctx = new (std::nothrow) zwz_ctx();
+    if (!ctx) return ZWZ_E_NOMEM;
+    ctx->device = device;
+    if (zwz_rt::device_props(device, &ctx->sm_count, &ctx->cc_major, &ctx->cc_minor, &ctx->total_mem, &ctx->smem_optin)) {
+        delete ctx;
+        return ZWZ_E_NODEVICE;
+    }
+#ifndef ZWZ_EMU
+    if (ctx->cc_major != 10) { // the fatbin holds sm_100a SASS only
+        delete ctx;
+        return ZWZ_E_NODEVICE;
+    }
+#endif
+    if (ctx->smem_optin < ZWZ_DM_SMEM_BYTES || zwz_rt::stream_create(&ctx->stream) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel, ZWZ_DM_SMEM_BYTES)) {
+        delete ctx;
+        return ZWZ_E_NODEVICE;
+    }
+    if (const char *e = getenv("ZWZ_BATCH_RAW_MB")) {
+        long v = atol(e);
+        if (v >= 1) ctx->batch_raw_bytes = (size_t) v << 20;
+    }
+    *out = ctx;
+    return ZWZ_OK;
+}
+
+void zwz_destroy(zwz_ctx *ctx) {
+    if (!ctx) return;
+    zwz_rt::set_device(ctx->device);
+    zwz_rt::stream_sync(ctx->stream);
+    release(ctx->meta);
+    release(ctx->scratch);
+    release(ctx->bulk_in);
+    release(ctx->bulk_out);
+    release(ctx->packed);
+    release(ctx->pin_meta);
+    release(ctx->counter);
+    zwz_rt::stream_destroy(ctx->stream);
+    delete ctx;
+}
+
+const char *zwz_last_error(const zwz_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int zwz_device_props(const zwz_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (total_mem) *total_mem = ctx->total_mem;
+    return ZWZ_OK;
+}
+
+uint64_t zwz_launch_count(const zwz_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int zwz_malloc_device(zwz_ctx *ctx, size_t bytes, void **ptr) {
+    if (!ctx || !ptr) return ZWZ_E_ARG;
+    zwz_rt::set_device(ctx->device);
+    return zwz_rt::malloc_device(ptr, bytes) ? fail(ctx, ZWZ_E_NOMEM, "device allocation failed") : ZWZ_OK;
+}
+int zwz_free_device(zwz_ctx *ctx, void *ptr) {
+    if (!ctx) return ZWZ_E_ARG;
+    zwz_rt::set_device(ctx->device);
+    zwz_rt::stream_sync(ctx->stream);
+    return zwz_rt::free_device(ptr) ? fail(ctx, ZWZ_E_CUDA, "cudaFree failed") : ZWZ_OK;
+}
+int zwz_malloc_pinned(zwz_ctx *ctx, size_t bytes, void **ptr) {
+    if (!ctx || !ptr) return ZWZ_E_ARG;
+    zwz_rt::set_device(ctx->device);
+    return zwz_rt::malloc_pinned(ptr, bytes) ? fail(ctx, ZWZ_E_NOMEM, "pinned allocation failed") : ZWZ_OK;
+}
+int zwz_free_pinned(zwz_ctx *ctx, void *ptr) {
+    if (!ctx) return ZWZ_E_ARG;
+    return zwz_rt::free_pinned(ptr) ? fail(ctx, ZWZ_E_CUDA, "cudaFreeHost failed") : ZWZ_OK;
+}
+int zwz_memcpy_h2d(zwz_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return ZWZ_E_ARG;
+    zwz_rt::set_device(ctx->device);
+    if (zwz_rt::memcpy_h2d(dst, src, bytes, ctx->stream) || zwz_rt::stream_sync(ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "h2d copy failed");
+    return ZWZ_OK;
+}
+int zwz_memcpy_d2h(zwz_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return ZWZ_E_ARG;
+    zwz_rt::set_device(ctx->device);
+    if (zwz_rt::memcpy_d2h(dst, src, bytes, ctx->stream) || zwz_rt::stream_sync(ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "d2h copy failed");
+    return ZWZ_OK;
+}
+int zwz_sync(zwz_ctx *ctx) {
+    if (!ctx) return ZWZ_E_ARG;
+    return zwz_rt::stream_sync(ctx->stream) ? fail(ctx, ZWZ_E_CUDA, "stream sync failed") : ZWZ_OK;
+}
+
+// ======================================================================================================================
+// deflate
+// ======================================================================================================================
+int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *d_out,
+                             const uint64_t *out_off, zwz_deflate_result *res, int level, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !out_off || !res || !d_out) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    uint64_t total_raw = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (len[i] > ZWZ_CHUNK_SIZE) return fail(ctx, ZWZ_E_ARG, "chunk longer than 65535 bytes");
+        if (out_off[i] & 3u) return fail(ctx, ZWZ_E_ARG, "out_off must be a multiple of 4");
+        total_raw += len[i];
+    }
+    if (total_raw && !d_raw) return fail(ctx, ZWZ_E_ARG, "null raw buffer");
+
+    // descriptors: [raw_off u64][scr_off u64][out_off u64][raw_len u32] per chunk, then results + adler on the device
+    const size_t meta_bytes = (size_t) n * (8 + 8 + 8 + 4);
+    const size_t dev_meta_bytes = align_up(meta_bytes, 256) + (size_t) n * 16 + (size_t) n * 4 + 256;
+    int rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 16), true))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, dev_meta_bytes, false))) return rc;
+    if ((rc = reserve(ctx, ctx->counter, 256, false))) return rc;
+
+    uint64_t *h_raw_off = (uint64_t *) ctx->pin_meta.p;
+    uint64_t *h_scr_off = h_raw_off + n;
+    uint64_t *h_out_off = h_scr_off + n;
+    uint32_t *h_len = (uint32_t *) (h_out_off + n);
+
+    // sub-batches bounded by scratch: scratch offsets restart at 0 in every sub-batch
+    std::vector<uint32_t> sub_begin;
+    size_t max_scr = 0;
+    {
+        size_t scr = 0, raw = 0;
+        sub_begin.push_back(0);
+        for (uint32_t i = 0; i < n; ++i) {
+            if (raw + len[i] > ctx->batch_raw_bytes && i > sub_begin.back()) {
+                max_scr = std::max(max_scr, scr);
+                sub_begin.push_back(i);
+                scr = 0;
+                raw = 0;
+            }
+            h_raw_off[i] = off[i];
+            h_scr_off[i] = scr;
+            h_out_off[i] = out_off[i];
+            h_len[i] = len[i];
+            scr += align_up((size_t) len[i] + 2, 32); // uint32 entries; +1 so the parser may peek one past the end
+            raw += len[i];
+        }
+        max_scr = std::max(max_scr, scr);
+        sub_begin.push_back(n);
+    }
+    if ((rc = reserve(ctx, ctx->scratch, max_scr * 4 + 256, false))) return rc;
+
+    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    if (zwz_rt::memcpy_h2d(dm, ctx->pin_meta.p, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    uint32_t *d_res = (uint32_t *) (dm + align_up(meta_bytes, 256));
+    uint32_t *d_adler = d_res + (size_t) n * 4;
+
+    const LevelParams lp = level_params(level);
+    for (size_t s = 0; s + 1 < sub_begin.size(); ++s) {
+        uint32_t b = sub_begin[s], e = sub_begin[s + 1];
+        zwz::DeflateJob job;
+        job.raw = d_raw;
+        job.raw_off = (const uint64_t *) dm + b;
+        job.scr_off = (const uint64_t *) dm + n + b;
+        job.out_off = (const uint64_t *) dm + 2 * (size_t) n + b;
+        job.raw_len = (const uint32_t *) ((const uint64_t *) dm + 3 * (size_t) n) + b;
+        job.scratch = (uint32_t *) ctx->scratch.p;
+        job.adler = d_adler + b;
+        job.out = d_out;
+        job.res = d_res + (size_t) b * 4;
+        job.n = e - b;
+        job.depth = lp.depth;
+        job.nice = lp.nice;
+        job.work_counter = (uint32_t *) ctx->counter.p;
+        if (zwz_rt::memset_device(ctx->counter.p, 0, 4, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
+        uint32_t grid1 = std::min<uint32_t>(job.n, (uint32_t) ctx->sm_count);
+        ZWZ_LAUNCH(zwz::lz_match_kernel, grid1, ZWZ_DM_THREADS, ZWZ_DM_SMEM_BYTES, st, job);
+        if ((rc = check_launch(ctx, "lz_match_kernel"))) return rc;
+        uint32_t grid2 = (job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS;
+        ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job);
+        if ((rc = check_launch(ctx, "deflate_encode_kernel"))) return rc;
+    }
+    // results come back through the pinned arena (descriptors are no longer needed once the kernels are queued ... but
+    // the H2D above must have completed before we overwrite it: same stream => ordered)
+    if (zwz_rt::memcpy_d2h(ctx->pin_meta.p, d_res, (size_t) n * 16, st) || zwz_rt::stream_sync(st))
+        return fail(ctx, ZWZ_E_CUDA, "deflate kernels failed");
+    memcpy(res, ctx->pin_meta.p, (size_t) n * 16);
+    return ZWZ_OK;
+}
+
+int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
+                      uint64_t *packed_off, zwz_deflate_result *res, int level) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
+    packed_off[0] = 0;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !res || !out) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    // span of the host buffer the chunks touch
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (len[i] > ZWZ_CHUNK_SIZE) return fail(ctx, ZWZ_E_ARG, "chunk longer than 65535 bytes");
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    if (hi < lo) lo = hi = 0;
+    std::vector<uint64_t> roff(n), slot(n + 1);
+    slot[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        roff[i] = off[i] - lo;
+        slot[i + 1] = slot[i] + zwz_deflate_bound(len[i]);
+    }
+    int rc;
+    if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
+    if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
+    if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, raw + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "raw upload failed");
+    if ((rc = zwz_deflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, roff.data(), len, n, (uint8_t *) ctx->bulk_out.p, slot.data(), res,
+                                       level, nullptr)))
+        return rc;
+    for (uint32_t i = 0; i < n; ++i) packed_off[i + 1] = packed_off[i] + res[i].len0 + res[i].len1;
+    if (packed_off[n] > out_cap) return fail(ctx, ZWZ_E_CAPACITY, "output buffer too small");
+    // gather on the device so only the compressed bytes cross the bus
+    const size_t pm = (size_t) (n + 1) * 8;
+    if ((rc = reserve(ctx, ctx->packed, (size_t) packed_off[n] + align_up(pm, 256) + 256, false))) return rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, pm, true))) return rc;
+    memcpy(ctx->pin_meta.p, packed_off, pm);
+    uint8_t *d_poff = (uint8_t *) ctx->packed.p;
+    uint8_t *d_packed = d_poff + align_up(pm, 256);
+    if (zwz_rt::memcpy_h2d(d_poff, ctx->pin_meta.p, pm, ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "offset upload failed");
+    // slot offsets and results are still in ctx->meta from the call above
+    const uint8_t *dm = (const uint8_t *) ctx->meta.p;
+    const uint64_t *d_slot_off = (const uint64_t *) dm + 2 * (size_t) n;
+    const uint32_t *d_res = (const uint32_t *) (dm + align_up((size_t) n * 28, 256));
+    ZWZ_LAUNCH(zwz::pack_streams_kernel, (n + 7) / 8, 256, 0, ctx->stream, (const uint8_t *) ctx->bulk_out.p, d_slot_off, d_res, d_packed,
+               (const uint64_t *) d_poff, n);
+    if ((rc = check_launch(ctx, "pack_streams_kernel"))) return rc;
+    if (zwz_rt::memcpy_d2h(out, d_packed, (size_t) packed_off[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
+        return fail(ctx, ZWZ_E_CUDA, "compressed download failed");
+    return ZWZ_OK;
+}
+
+// ======================================================================================================================
+// inflate
+// ======================================================================================================================
+int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *d_raw_out,
+                             const uint64_t *raw_off, uint32_t *raw_len, uint32_t *status, uint32_t flags, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !raw_off || !raw_len || !status) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    const size_t m_off = 0, m_roff = (size_t) n * 8, m_len = m_roff + (size_t) (n + 1) * 8, meta_bytes = m_len + (size_t) n * 4;
+    const size_t r_base = align_up(meta_bytes, 256);
+    int rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 8), true))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 8 + 256, false))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    memcpy(hp + m_off, off, (size_t) n * 8);
+    memcpy(hp + m_roff, raw_off, (size_t) (n + 1) * 8);
+    memcpy(hp + m_len, len, (size_t) n * 4);
+    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    uint32_t *d_rlen = (uint32_t *) (dm + r_base);
+    uint32_t *d_stat = d_rlen + n;
+    ZWZ_LAUNCH(zwz::inflate_kernel, (n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
+               (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags);
+    if ((rc = check_launch(ctx, "inflate_kernel"))) return rc;
+    if (zwz_rt::memcpy_d2h(hp, d_rlen, (size_t) n * 8, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "inflate kernel failed");
+    memcpy(raw_len, hp, (size_t) n * 4);
+    memcpy(status, hp + (size_t) n * 4, (size_t) n * 4);
+    return ZWZ_OK;
+}
+
+int zwz_inflate_batch(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *raw_out,
+                      const uint64_t *raw_off, uint32_t *raw_len, uint32_t *status, uint32_t flags) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !raw_off || !raw_len || !status) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    if (hi < lo) lo = hi = 0;
+    std::vector<uint64_t> coff(n), roff(n + 1);
+    for (uint32_t i = 0; i < n; ++i) coff[i] = off[i] - lo;
+    for (uint32_t i = 0; i <= n; ++i) roff[i] = raw_off[i] - raw_off[0];
+    int rc;
+    if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
+    if ((rc = reserve(ctx, ctx->bulk_out, (size_t) roff[n] + 64, false))) return rc;
+    if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, comp + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "compressed upload failed");
+    if ((rc = zwz_inflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, coff.data(), len, n, (uint8_t *) ctx->bulk_out.p, roff.data(), raw_len,
+                                       status, flags, nullptr)))
+        return rc;
+    if (zwz_rt::memcpy_d2h(raw_out + raw_off[0], ctx->bulk_out.p, (size_t) roff[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
+        return fail(ctx, ZWZ_E_CUDA, "raw download failed");
+    return ZWZ_OK;
+}
+
+// ======================================================================================================================
+// MD5 / Adler-32
+// ======================================================================================================================
+static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
+                      uint32_t n, uint8_t *digest, int finalize, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || (finalize && !digest)) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    const size_t m_len = (size_t) n * 8, m_tot = 2 * (size_t) n * 8, m_state = 3 * (size_t) n * 8, meta_bytes = m_state + (size_t) n * 16;
+    const size_t r_base = align_up(meta_bytes, 256);
+    int rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 16 + 256, false))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    memcpy(hp, off, (size_t) n * 8);
+    memcpy(hp + m_len, len, (size_t) n * 8);
+    if (total_len) memcpy(hp + m_tot, total_len, (size_t) n * 8);
+    if (state) memcpy(hp + m_state, state, (size_t) n * 16);
+    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    uint8_t *d_digest = dm + r_base;
+    ZWZ_LAUNCH(zwz::md5_files_kernel, (n + 127) / 128, 128, 0, st, d_data, (const uint64_t *) dm, (const uint64_t *) (dm + m_len),
+               total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr, state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr,
+               d_digest, n, finalize);
+    if ((rc = check_launch(ctx, "md5_files_kernel"))) return rc;
+    if (finalize && zwz_rt::memcpy_d2h(hp, d_digest, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "digest download failed");
+    if (state && zwz_rt::memcpy_d2h(hp + m_state, dm + m_state, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "state download failed");
+    if (zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "md5 kernel failed");
+    if (finalize) memcpy(digest, hp, (size_t) n * 16);
+    if (state) memcpy(state, hp + m_state, (size_t) n * 16);
+    return ZWZ_OK;
+}
+
+int zwz_md5_batch_device(zwz_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *digest, void *stream) {
+    return md5_launch(ctx, nullptr, d_data, off, len, nullptr, n, digest, 1, stream);
+}
+
+int zwz_md5_batch(zwz_ctx *ctx, const uint8_t *data, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *digest) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !digest) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    if (hi < lo) lo = hi = 0;
+    std::vector<uint64_t> o(n);
+    for (uint32_t i = 0; i < n; ++i) o[i] = off[i] - lo;
+    int rc;
+    if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
+    if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, data + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "data upload failed");
+    return md5_launch(ctx, nullptr, (const uint8_t *) ctx->bulk_in.p, o.data(), len, nullptr, n, digest, 1, nullptr);
+}
+
+void zwz_md5_state_init(uint32_t *state, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) {
+        state[4 * i + 0] = 0x67452301u;
+        state[4 * i + 1] = 0xefcdab89u;
+        state[4 * i + 2] = 0x98badcfeu;
+        state[4 * i + 3] = 0x10325476u;
+    }
+}
+
+int zwz_md5_update_device(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, uint32_t n, void *stream) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!state) return fail(ctx, ZWZ_E_ARG, "null state");
+    for (uint32_t i = 0; i < n; ++i)
+        if (len[i] & 63u) return fail(ctx, ZWZ_E_ARG, "md5 update length must be a multiple of 64");
+    return md5_launch(ctx, state, d_data, off, len, nullptr, n, nullptr, 0, stream);
+}
+
+int zwz_md5_final_device(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_tail, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
+                         uint32_t n, uint8_t *digest, void *stream) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!state || !total_len) return fail(ctx, ZWZ_E_ARG, "null argument");
+    return md5_launch(ctx, state, d_tail, off, len, total_len, n, digest, 1, stream);
+}
+
+void zwz_md5_hex(const uint8_t digest[16], char hex[32]) {
+    static const char d[] = "0123456789abcdef";
+    for (int i = 0; i < 16; ++i) {
+        hex[2 * i] = d[digest[i] >> 4];
+        hex[2 * i + 1] = d[digest[i] & 15];
+    }
+}
+
+int zwz_adler32_batch_device(zwz_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t *adler, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || !adler) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    const size_t m_len = (size_t) n * 8, meta_bytes = m_len + (size_t) n * 4, r_base = align_up(meta_bytes, 256);
+    int rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 4 + 256, false))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    memcpy(hp, off, (size_t) n * 8);
+    memcpy(hp + m_len, len, (size_t) n * 4);
+    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    ZWZ_LAUNCH(zwz::adler32_kernel, (n + 7) / 8, 256, 0, st, d_data, (const uint64_t *) dm, (const uint32_t *) (dm + m_len), (uint32_t *) (dm + r_base), n);
+    if ((rc = check_launch(ctx, "adler32_kernel"))) return rc;
+    if (zwz_rt::memcpy_d2h(hp, dm + r_base, (size_t) n * 4, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "adler kernel failed");
+    memcpy(adler, hp, (size_t) n * 4);
+    return ZWZ_OK;
+}
+
+} // extern "C"

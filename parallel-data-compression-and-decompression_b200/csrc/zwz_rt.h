@@ -1,0 +1,94 @@
+// zwz_rt.h — the handful of CUDA runtime calls the C ABI needs, behind one seam.
+//
+// Product build (nvcc): thin inline wrappers over the CUDA runtime.
+// Emulator build (-DZWZ_EMU, tests only): "device" memory is host memory and a launch runs the kernel body through
+// tests/simt/simt_emu.h. The emulator library is never loaded by the product package.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#ifdef ZWZ_EMU
+typedef void *zwz_stream_t;
+namespace zwz_rt {
+inline const char *backend() { return "simt-emulator"; }
+inline int device_count() { return 1; }
+inline int set_device(int) { return 0; }
+inline int device_props(int, int *sms, int *maj, int *min, size_t *mem, size_t *smem_optin) {
+    *sms = 4;
+    *maj = 10;
+    *min = 0;
+    *mem = (size_t) 1 << 34;
+    *smem_optin = 232448;
+    return 0;
+}
+inline int malloc_device(void **p, size_t n) {
+    *p = malloc(n ? n : 1);
+    if (*p) memset(*p, 0xCD, n); // cudaMalloc memory is not zeroed either
+    return *p ? 0 : 2;
+}
+inline int free_device(void *p) { free(p); return 0; }
+inline int malloc_pinned(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+inline int free_pinned(void *p) { free(p); return 0; }
+inline int stream_create(zwz_stream_t *s) { *s = nullptr; return 0; }
+inline int stream_destroy(zwz_stream_t) { return 0; }
+inline int stream_sync(zwz_stream_t) { return 0; }
+inline int memcpy_h2d(void *d, const void *s, size_t n, zwz_stream_t) { if (n) memcpy(d, s, n); return 0; }
+inline int memcpy_d2h(void *d, const void *s, size_t n, zwz_stream_t) { if (n) memcpy(d, s, n); return 0; }
+inline int memset_device(void *d, int v, size_t n, zwz_stream_t) { if (n) memset(d, v, n); return 0; }
+inline int last_error(std::string &) { return 0; }
+inline int set_max_dyn_smem(const void *, size_t) { return 0; }
+} // namespace zwz_rt
+#define ZWZ_LAUNCH(kern, grid, block, smem, stream, ...) simt::launch((unsigned) (grid), (unsigned) (block), (size_t) (smem), [&] { kern(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+typedef cudaStream_t zwz_stream_t;
+namespace zwz_rt {
+inline const char *backend() { return "cuda"; }
+inline int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+inline int set_device(int d) { return cudaSetDevice(d) == cudaSuccess ? 0 : 1; }
+inline int device_props(int d, int *sms, int *maj, int *min, size_t *mem, size_t *smem_optin) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) != cudaSuccess) return 1;
+    *sms = p.multiProcessorCount;
+    *maj = p.major;
+    *min = p.minor;
+    *mem = p.totalGlobalMem;
+    *smem_optin = p.sharedMemPerBlockOptin;
+    return 0;
+}
+inline int malloc_device(void **p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : 2; }
+inline int free_device(void *p) { return cudaFree(p) == cudaSuccess ? 0 : 1; }
+inline int malloc_pinned(void **p, size_t n) { return cudaMallocHost(p, n ? n : 1) == cudaSuccess ? 0 : 2; }
+inline int free_pinned(void *p) { return cudaFreeHost(p) == cudaSuccess ? 0 : 1; }
+inline int stream_create(zwz_stream_t *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1; }
+inline int stream_destroy(zwz_stream_t s) { return cudaStreamDestroy(s) == cudaSuccess ? 0 : 1; }
+inline int stream_sync(zwz_stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 1; }
+inline int memcpy_h2d(void *d, const void *s, size_t n, zwz_stream_t st) {
+    return n == 0 || cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : 1;
+}
+inline int memcpy_d2h(void *d, const void *s, size_t n, zwz_stream_t st) {
+    return n == 0 || cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st) == cudaSuccess ? 0 : 1;
+}
+inline int memset_device(void *d, int v, size_t n, zwz_stream_t st) { return n == 0 || cudaMemsetAsync(d, v, n, st) == cudaSuccess ? 0 : 1; }
+inline int last_error(std::string &msg) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    msg = cudaGetErrorString(e);
+    return 1;
+}
+inline int set_max_dyn_smem(const void *fn, size_t bytes) {
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) == cudaSuccess ? 0 : 1;
+}
+} // namespace zwz_rt
+#define ZWZ_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
