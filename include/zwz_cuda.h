@@ -82,6 +82,19 @@ int zwz_sync(zwz_ctx *ctx);
 /* number of kernel launches this ctx has issued so far (bench.py's gpu_launches) */
 uint64_t zwz_launch_count(const zwz_ctx *ctx);
 
+/* Per-kernel device timing (CUDA events recorded on the launching stream around every kernel of this ctx). Used by
+ * bench.py for the roofline line; off by default. zwz_profile_read syncs, then returns the accumulated milliseconds and
+ * launch counts per kernel kind since the last reset. */
+#define ZWZ_PROF_MATCH 0   /* lz_match_kernel        */
+#define ZWZ_PROF_ENCODE 1  /* deflate_encode_kernel  */
+#define ZWZ_PROF_INFLATE 2 /* inflate_kernel         */
+#define ZWZ_PROF_MD5 3     /* md5_files_kernel       */
+#define ZWZ_PROF_PACK 4    /* pack_streams_kernel    */
+#define ZWZ_PROF_ADLER 5   /* adler32_kernel         */
+#define ZWZ_PROF_N 6
+int zwz_profile_enable(zwz_ctx *ctx, int on);
+int zwz_profile_read(zwz_ctx *ctx, double *ms /* [ZWZ_PROF_N] */, uint64_t *launches /* [ZWZ_PROF_N] */, int reset);
+
 /* ---- deflate: compression.cpp:119-134 ---------------------------------------------------------------------------- */
 static inline uint64_t zwz_deflate_bound(uint32_t raw_len) { return (((uint64_t) raw_len + ZWZ_DEFLATE_MARGIN) + 15u) & ~(uint64_t) 15u; }
 
@@ -95,6 +108,12 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
  * (packed_off has n+1 entries and is filled by the call). out_cap >= sum(zwz_deflate_bound(len[i])) always suffices. */
 int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n,
                       uint8_t *out, uint64_t out_cap, uint64_t *packed_off, zwz_deflate_result *res, int level);
+
+/* Gather the variable-length streams of a finished zwz_deflate_batch_device out of their slots into one packed device
+ * buffer (what the host then writes as record payloads, compression.cpp:93): chunk i's stream(s) land at
+ * d_packed + packed_off[i] .. packed_off[i+1]; packed_off (host, n+1 entries) is filled by the call. */
+int zwz_pack_streams_device(zwz_ctx *ctx, const uint8_t *d_slots, const uint64_t *slot_off, const zwz_deflate_result *res, uint32_t n,
+                            uint8_t *d_packed, uint64_t *packed_off, void *stream);
 
 /* ---- inflate: decompression.cpp:11-37 ---------------------------------------------------------------------------- */
 /* Stream i is comp[off[i] .. off[i]+len[i]) (a complete RFC 1950 stream, or a truncated one). Output goes to

@@ -68,6 +68,7 @@ def _declare(L):
     L.zwz_sync.argtypes = [vp]
     L.zwz_deflate_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, i32, vp]
     L.zwz_deflate_batch.argtypes = [vp, vp, vp, vp, u32, vp, u64, vp, vp, i32]
+    L.zwz_pack_streams_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.zwz_inflate_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, u32, vp]
     L.zwz_inflate_batch.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, u32]
     L.zwz_md5_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp]
@@ -79,6 +80,8 @@ def _declare(L):
     L.zwz_md5_hex.argtypes = [vp, vp]
     L.zwz_md5_hex.restype = None
     L.zwz_adler32_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp]
+    L.zwz_profile_enable.argtypes = [vp, i32]
+    L.zwz_profile_read.argtypes = [vp, vp, vp, i32]
     return L
 
 
@@ -170,6 +173,18 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.zwz_launch_count(self.h))
 
+    PROF_KINDS = ("lz_match", "deflate_encode", "inflate", "md5", "pack", "adler32")
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.zwz_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True):
+        """{kernel: (milliseconds, launches)} measured with CUDA events on the launching stream since the last reset."""
+        ms = np.zeros(len(self.PROF_KINDS), dtype=np.float64)
+        cnt = np.zeros(len(self.PROF_KINDS), dtype=np.uint64)
+        self._check(self.lib.zwz_profile_read(self.h, ms.ctypes.data, cnt.ctypes.data, 1 if reset else 0))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_KINDS)}
+
     def props(self):
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._check(self.lib.zwz_device_props(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
@@ -217,6 +232,15 @@ class Context:
         self._check(self.lib.zwz_deflate_batch_device(self.h, d_raw, _ptr(off), _ptr(length), n, d_out, _ptr(out_off), _ptr(res), level,
                                                       stream or None))
         return res
+
+    def pack_streams_device(self, d_slots: int, slot_off, res, d_packed: int, stream: int = 0) -> np.ndarray:
+        """Slots -> packed payload bytes on the device; returns packed_off[n+1]."""
+        slot_off = np.ascontiguousarray(slot_off, dtype=np.uint64)
+        res = np.ascontiguousarray(res)
+        n = len(slot_off)
+        poff = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self.lib.zwz_pack_streams_device(self.h, d_slots, _ptr(slot_off), _ptr(res), n, d_packed, poff.ctypes.data, stream or None))
+        return poff
 
     # ---- inflate: decompression.cpp:11-37 ----
     def inflate_batch(self, comp, off, length, raw_off, flags: int = 0):
@@ -266,20 +290,18 @@ class Context:
         state = np.zeros(4, dtype=np.uint32)
         self.lib.zwz_md5_state_init(_ptr(state), 1)
         piece -= piece % 64
+        off = np.zeros(1, dtype=np.uint64)   # kept alive across the calls: ctypes only sees their addresses
+        ln = np.zeros(1, dtype=np.uint64)
+        tot = np.array([total_len], dtype=np.uint64)
         done = 0
-        while total_len - done > piece:
-            self._check(self.lib.zwz_md5_update_device(self.h, _ptr(state), d_data, _ptr(np.array([done], dtype=np.uint64)),
-                                                       _ptr(np.array([piece], dtype=np.uint64)), 1, None))
-            done += piece
-        full = (total_len - done) // 64 * 64
-        if full:
-            self._check(self.lib.zwz_md5_update_device(self.h, _ptr(state), d_data, _ptr(np.array([done], dtype=np.uint64)),
-                                                       _ptr(np.array([full], dtype=np.uint64)), 1, None))
-            done += full
+        while total_len - done >= 64:
+            step = min(piece, (total_len - done) // 64 * 64)
+            off[0], ln[0] = done, step
+            self._check(self.lib.zwz_md5_update_device(self.h, _ptr(state), d_data, _ptr(off), _ptr(ln), 1, None))
+            done += step
         dg = np.zeros(16, dtype=np.uint8)
-        self._check(self.lib.zwz_md5_final_device(self.h, _ptr(state), d_data, _ptr(np.array([done], dtype=np.uint64)),
-                                                  _ptr(np.array([total_len - done], dtype=np.uint64)),
-                                                  _ptr(np.array([total_len], dtype=np.uint64)), 1, _ptr(dg), None))
+        off[0], ln[0] = done, total_len - done
+        self._check(self.lib.zwz_md5_final_device(self.h, _ptr(state), d_data, _ptr(off), _ptr(ln), _ptr(tot), 1, _ptr(dg), None))
         return dg.tobytes()
 
     def adler32_batch_device(self, d_data: int, off, length, stream: int = 0) -> np.ndarray:

@@ -63,6 +63,15 @@ struct zwz_ctx {
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, counter;
     size_t batch_raw_bytes = (size_t) 1 << 30; // raw bytes per internal deflate sub-batch (scratch = 4x that)
+    // optional per-kernel timing
+    bool profiling = false;
+    struct Span {
+        int kind;
+        zwz_rt::zwz_event_t a, b;
+    };
+    std::vector<Span> spans;
+    double prof_ms[ZWZ_PROF_N] = {0};
+    uint64_t prof_n[ZWZ_PROF_N] = {0};
 };
 
 namespace {
@@ -106,6 +115,24 @@ void release(Arena &a) {
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// RAII bracket: records an event pair around one kernel launch when profiling is on
+struct ProfSpan {
+    zwz_ctx *ctx;
+    zwz_stream_t st;
+    zwz_ctx::Span sp;
+    bool on;
+    ProfSpan(zwz_ctx *c, int kind, zwz_stream_t s) : ctx(c), st(s), on(c->profiling) {
+        sp.kind = kind;
+        if (on) zwz_rt::event_record(&sp.a, st);
+    }
+    ~ProfSpan() {
+        if (on) {
+            zwz_rt::event_record(&sp.b, st);
+            ctx->spans.push_back(sp);
+        }
+    }
+};
 
 int check_launch(zwz_ctx *ctx, const char *what) {
     ctx->launches++;
@@ -192,6 +219,32 @@ int zwz_device_props(const zwz_ctx *ctx, int *sm_count, int *cc_major, int *cc_m
 }
 
 uint64_t zwz_launch_count(const zwz_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int zwz_profile_enable(zwz_ctx *ctx, int on) {
+    if (!ctx) return ZWZ_E_ARG;
+    ctx->profiling = on != 0;
+    return ZWZ_OK;
+}
+int zwz_profile_read(zwz_ctx *ctx, double *ms, uint64_t *launches, int reset) {
+    if (!ctx) return ZWZ_E_ARG;
+#ifndef ZWZ_EMU
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(ctx, ZWZ_E_CUDA, "device sync failed");
+#endif
+    for (auto &sp : ctx->spans) {
+        ctx->prof_ms[sp.kind] += zwz_rt::event_elapsed_and_free(sp.a, sp.b);
+        ctx->prof_n[sp.kind] += 1;
+    }
+    ctx->spans.clear();
+    for (int k = 0; k < ZWZ_PROF_N; ++k) {
+        if (ms) ms[k] = ctx->prof_ms[k];
+        if (launches) launches[k] = ctx->prof_n[k];
+        if (reset) {
+            ctx->prof_ms[k] = 0;
+            ctx->prof_n[k] = 0;
+        }
+    }
+    return ZWZ_OK;
+}
 
 int zwz_malloc_device(zwz_ctx *ctx, size_t bytes, void **ptr) {
     if (!ctx || !ptr) return ZWZ_E_ARG;
@@ -310,10 +363,16 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         job.work_counter = (uint32_t *) ctx->counter.p;
         if (zwz_rt::memset_device(ctx->counter.p, 0, 4, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
         uint32_t grid1 = std::min<uint32_t>(job.n, (uint32_t) ctx->sm_count);
-        ZWZ_LAUNCH(zwz::lz_match_kernel, grid1, ZWZ_DM_THREADS, ZWZ_DM_SMEM_BYTES, st, job);
+        {
+            ProfSpan ps(ctx, ZWZ_PROF_MATCH, st);
+            ZWZ_LAUNCH(zwz::lz_match_kernel, grid1, ZWZ_DM_THREADS, ZWZ_DM_SMEM_BYTES, st, job);
+        }
         if ((rc = check_launch(ctx, "lz_match_kernel"))) return rc;
         uint32_t grid2 = (job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS;
-        ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job);
+        {
+            ProfSpan ps(ctx, ZWZ_PROF_ENCODE, st);
+            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job);
+        }
         if ((rc = check_launch(ctx, "deflate_encode_kernel"))) return rc;
     }
     // results come back through the pinned arena (descriptors are no longer needed once the kernels are queued ... but
@@ -367,11 +426,44 @@ int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, con
     const uint8_t *dm = (const uint8_t *) ctx->meta.p;
     const uint64_t *d_slot_off = (const uint64_t *) dm + 2 * (size_t) n;
     const uint32_t *d_res = (const uint32_t *) (dm + align_up((size_t) n * 28, 256));
-    ZWZ_LAUNCH(zwz::pack_streams_kernel, (n + 7) / 8, 256, 0, ctx->stream, (const uint8_t *) ctx->bulk_out.p, d_slot_off, d_res, d_packed,
-               (const uint64_t *) d_poff, n);
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_PACK, ctx->stream);
+        ZWZ_LAUNCH(zwz::pack_streams_kernel, (n + 7) / 8, 256, 0, ctx->stream, (const uint8_t *) ctx->bulk_out.p, d_slot_off, d_res, d_packed,
+                   (const uint64_t *) d_poff, n);
+    }
     if ((rc = check_launch(ctx, "pack_streams_kernel"))) return rc;
     if (zwz_rt::memcpy_d2h(out, d_packed, (size_t) packed_off[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
         return fail(ctx, ZWZ_E_CUDA, "compressed download failed");
+    return ZWZ_OK;
+}
+
+int zwz_pack_streams_device(zwz_ctx *ctx, const uint8_t *d_slots, const uint64_t *slot_off, const zwz_deflate_result *res, uint32_t n,
+                            uint8_t *d_packed, uint64_t *packed_off, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
+    packed_off[0] = 0;
+    if (n == 0) return ZWZ_OK;
+    if (!slot_off || !res || !d_slots || !d_packed) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    for (uint32_t i = 0; i < n; ++i) packed_off[i + 1] = packed_off[i] + res[i].len0 + res[i].len1;
+    const size_t m_poff = (size_t) n * 8, m_res = m_poff + (size_t) (n + 1) * 8, meta_bytes = m_res + (size_t) n * 16;
+    int rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, meta_bytes + 256, false))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    memcpy(hp, slot_off, (size_t) n * 8);
+    memcpy(hp + m_poff, packed_off, (size_t) (n + 1) * 8);
+    memcpy(hp + m_res, res, (size_t) n * 16);
+    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_PACK, st);
+        ZWZ_LAUNCH(zwz::pack_streams_kernel, (n + 7) / 8, 256, 0, st, d_slots, (const uint64_t *) dm, (const uint32_t *) (dm + m_res), d_packed,
+                   (const uint64_t *) (dm + m_poff), n);
+    }
+    if ((rc = check_launch(ctx, "pack_streams_kernel"))) return rc;
+    if (zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "pack kernel failed");
     return ZWZ_OK;
 }
 
@@ -398,8 +490,11 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint32_t *d_rlen = (uint32_t *) (dm + r_base);
     uint32_t *d_stat = d_rlen + n;
-    ZWZ_LAUNCH(zwz::inflate_kernel, (n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
-               (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags);
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_INFLATE, st);
+        ZWZ_LAUNCH(zwz::inflate_kernel, (n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
+                   (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags);
+    }
     if ((rc = check_launch(ctx, "inflate_kernel"))) return rc;
     if (zwz_rt::memcpy_d2h(hp, d_rlen, (size_t) n * 8, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "inflate kernel failed");
     memcpy(raw_len, hp, (size_t) n * 4);
@@ -457,9 +552,12 @@ static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, cons
     uint8_t *dm = (uint8_t *) ctx->meta.p;
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint8_t *d_digest = dm + r_base;
-    ZWZ_LAUNCH(zwz::md5_files_kernel, (n + 127) / 128, 128, 0, st, d_data, (const uint64_t *) dm, (const uint64_t *) (dm + m_len),
-               total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr, state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr,
-               d_digest, n, finalize);
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_MD5, st);
+        ZWZ_LAUNCH(zwz::md5_files_kernel, (n + 127) / 128, 128, 0, st, d_data, (const uint64_t *) dm, (const uint64_t *) (dm + m_len),
+                   total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr,
+                   state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr, d_digest, n, finalize);
+    }
     if ((rc = check_launch(ctx, "md5_files_kernel"))) return rc;
     if (finalize && zwz_rt::memcpy_d2h(hp, d_digest, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "digest download failed");
     if (state && zwz_rt::memcpy_d2h(hp + m_state, dm + m_state, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "state download failed");
@@ -539,7 +637,11 @@ int zwz_adler32_batch_device(zwz_ctx *ctx, const uint8_t *d_data, const uint64_t
     memcpy(hp + m_len, len, (size_t) n * 4);
     uint8_t *dm = (uint8_t *) ctx->meta.p;
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
-    ZWZ_LAUNCH(zwz::adler32_kernel, (n + 7) / 8, 256, 0, st, d_data, (const uint64_t *) dm, (const uint32_t *) (dm + m_len), (uint32_t *) (dm + r_base), n);
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_ADLER, st);
+        ZWZ_LAUNCH(zwz::adler32_kernel, (n + 7) / 8, 256, 0, st, d_data, (const uint64_t *) dm, (const uint32_t *) (dm + m_len),
+                   (uint32_t *) (dm + r_base), n);
+    }
     if ((rc = check_launch(ctx, "adler32_kernel"))) return rc;
     if (zwz_rt::memcpy_d2h(hp, dm + r_base, (size_t) n * 4, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "adler kernel failed");
     memcpy(adler, hp, (size_t) n * 4);

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <time.h>
 
 #ifdef ZWZ_EMU
 typedef void *zwz_stream_t;
@@ -40,6 +41,14 @@ inline int memcpy_d2h(void *d, const void *s, size_t n, zwz_stream_t) { if (n) m
 inline int memset_device(void *d, int v, size_t n, zwz_stream_t) { if (n) memset(d, v, n); return 0; }
 inline int last_error(std::string &) { return 0; }
 inline int set_max_dyn_smem(const void *, size_t) { return 0; }
+typedef double zwz_event_t; // wall-clock stamp
+inline int event_record(zwz_event_t *e, zwz_stream_t) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    *e = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    return 0;
+}
+inline double event_elapsed_and_free(zwz_event_t a, zwz_event_t b) { return b - a; }
 } // namespace zwz_rt
 #define ZWZ_LAUNCH(kern, grid, block, smem, stream, ...) simt::launch((unsigned) (grid), (unsigned) (block), (size_t) (smem), [&] { kern(__VA_ARGS__); })
 #else
@@ -88,6 +97,18 @@ inline int last_error(std::string &msg) {
 }
 inline int set_max_dyn_smem(const void *fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) == cudaSuccess ? 0 : 1;
+}
+typedef cudaEvent_t zwz_event_t;
+inline int event_record(zwz_event_t *e, zwz_stream_t st) {
+    if (cudaEventCreate(e) != cudaSuccess) return 1;
+    return cudaEventRecord(*e, st) == cudaSuccess ? 0 : 1;
+}
+inline double event_elapsed_and_free(zwz_event_t a, zwz_event_t b) { // caller has synchronised
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return ms;
 }
 } // namespace zwz_rt
 #define ZWZ_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)

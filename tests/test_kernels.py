@@ -1,0 +1,286 @@
+"""Parity tests of the hot path THROUGH THE C ABI (include/zwz_cuda.h) against the oracle.
+
+Every test runs twice: `[emu]` here on the CPU (the kernel sources under the SIMT emulator, small inputs — checks the
+kernel logic before a GPU is spent on it) and `[cuda]` on the B200 (`-m gpu`, the product library libzwz_cuda.so).
+Bit-exact bars:
+  inflate  bytes, byte count and status == oracle (== zlib 1.3 as driven by decompression.cpp:11-37)
+  MD5      digest == oracle == OpenSSL
+  deflate  (1) oracle inflate AND the reference's zlib inflate both return the original bytes,
+           (4) size <= 1.03 x zlib level 6 per content class (BASELINE.json tolerance)
+"""
+import hashlib
+import json
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import zwz_format
+from tools import corpus
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CHUNK = 65535
+RATIO_TOLERANCE = 1.03  # north_star criterion (4)
+
+
+def _cat(parts):
+    off = np.zeros(len(parts) + 1, dtype=np.uint64)
+    np.cumsum([len(p) for p in parts], out=off[1:])
+    return b"".join(parts), off
+
+
+# ---------------------------------------------------------------------------------------------------------------- MD5
+def test_md5_rfc_and_padding(ctx):
+    files = [b"", b"a", b"abc", b"message digest", b"abcdefghijklmnopqrstuvwxyz", b"1234567890" * 8]
+    files += [bytes([i & 255]) * n for i, n in enumerate([55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 129, 1000, 4097])]
+    files += [corpus.gen_file(c, n, 596, 50 + i).tobytes() for i, (c, n) in enumerate([("T", 5000), ("R", 20011), ("B", 70001)])]
+    buf, off = _cat(files)
+    for shift in (0, 1, 2, 3):  # every byte alignment of the batch
+        data = b"\x00" * shift + buf
+        dg = ctx.md5_batch(data, off[:-1] + np.uint64(shift), np.diff(off))
+        for f, d in zip(files, dg):
+            assert bytes(d).hex() == O.md5_hex(f) == hashlib.md5(f).hexdigest()
+
+
+def test_md5_streaming_update_final(ctx):
+    raw = corpus.gen_text(300_000, 596, 9)
+    d = ctx.malloc_device(raw.nbytes + 64)
+    try:
+        ctx.h2d(d, raw)
+        assert ctx.md5_stream_device(d, raw.nbytes, piece=65536).hex() == hashlib.md5(raw.tobytes()).hexdigest()
+        assert ctx.md5_stream_device(d, 1000, piece=64).hex() == hashlib.md5(raw[:1000].tobytes()).hexdigest()
+        assert ctx.md5_stream_device(d, 128, piece=64).hex() == hashlib.md5(raw[:128].tobytes()).hexdigest()
+        assert ctx.md5_stream_device(d, 0).hex() == hashlib.md5(b"").hexdigest()
+    finally:
+        ctx.free_device(d)
+
+
+def test_adler32(ctx):
+    parts = [b"", b"a", b"Wikipedia", b"\xff" * 65535, corpus.gen_random(65535, 596, 1).tobytes(), corpus.gen_text(12345, 596, 2).tobytes()]
+    buf, off = _cat(parts)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    d = ctx.malloc_device(arr.nbytes + 64)
+    try:
+        ctx.h2d(d, arr)
+        got = ctx.adler32_batch_device(d, off[:-1], np.diff(off).astype(np.uint32))
+    finally:
+        ctx.free_device(d)
+    assert [int(x) for x in got] == [zlib.adler32(p) for p in parts] == [O.adler32(p) for p in parts]
+
+
+# ------------------------------------------------------------------------------------------------------------ inflate
+def _zlib_streams(sizes):
+    out = []
+    for i, (c, n) in enumerate(sizes):
+        raw = corpus.gen_file(c, n, 596, 100 + i).tobytes()
+        for lvl, strat, wb in [(6, 0, 15), (1, 0, 15), (9, 0, 15), (0, 0, 15), (6, zlib.Z_FIXED, 15), (6, zlib.Z_HUFFMAN_ONLY, 15),
+                               (6, zlib.Z_RLE, 15), (4, 0, 9)]:
+            co = zlib.compressobj(lvl, zlib.DEFLATED, wb, 8, strat)
+            out.append((raw, co.compress(raw) + co.flush()))
+    return out
+
+
+def _check_inflate(ctx, streams, cap):
+    comp, off = _cat(streams)
+    raw_off = (np.arange(len(streams) + 1, dtype=np.uint64) * np.uint64(cap))
+    out, rl, st = ctx.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
+    for i, s in enumerate(streams):
+        want, wst, wn = O.inflate(s, cap)
+        got = out[int(raw_off[i]):int(raw_off[i]) + min(int(rl[i]), cap)].tobytes()
+        assert (int(rl[i]), int(st[i])) == (wn, wst), (i, len(s))
+        assert got == want, (i, len(s))
+        assert got == O.ref_inflate_chunk(s)[:cap]  # and the reference's own zlib loop says the same
+
+
+def test_inflate_all_block_types(ctx, is_gpu):
+    sizes = [("T", 65535), ("S", 40000), ("B", 65535), ("R", 65535), ("J", 7000), ("T", 96), ("T", 0), ("T", 1)]
+    if not is_gpu:
+        sizes = [("T", 30000), ("S", 9000), ("B", 12000), ("R", 3000), ("J", 2000), ("T", 96), ("T", 0), ("T", 1)]
+    streams = [c for _, c in _zlib_streams(sizes)]
+    _check_inflate(ctx, streams, 70000)
+
+
+def test_inflate_truncated_and_corrupted(ctx, is_gpu):
+    rng = random.Random(7)
+    sizes = [("T", 20000), ("S", 9000), ("B", 9000), ("R", 3000), ("T", 50)] if not is_gpu else [("T", 65535), ("S", 40000), ("B", 65535), ("R", 30000), ("T", 50)]
+    cases = []
+    reps = 3 if not is_gpu else 12
+    for _, comp in _zlib_streams(sizes):
+        for _ in range(reps):
+            cases.append(comp[:rng.randrange(0, len(comp) + 1)])
+            cb = bytearray(comp)
+            for _ in range(rng.randrange(1, 3)):
+                cb[rng.randrange(len(cb))] ^= 1 << rng.randrange(8)
+            cases.append(bytes(cb))
+    cases += [b"", b"\x78", b"\x78\x9c", b"\x78\x9c\x03", b"\x78\x9d\x03\x00", b"\x00" * 10, b"\xff" * 10, b"\x78\x9c\x07"]
+    _check_inflate(ctx, cases, 70000)
+
+
+def test_inflate_output_capacity(ctx):
+    raw = corpus.gen_text(9000, 596, 3).tobytes()
+    streams = [zlib.compress(raw), zlib.compress(raw[:100]), zlib.compress(b"")]
+    comp, off = _cat(streams)
+    raw_off = np.array([0, 1000, 1100, 1100], dtype=np.uint64)
+    out, rl, st = ctx.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
+    assert list(st) == [O.STREAM_OUTPUT_FULL, O.STREAM_END, O.STREAM_END]
+    assert list(rl) == [9000, 100, 0]
+    assert out[:1000].tobytes() == raw[:1000] and out[1000:1100].tobytes() == raw[:100]
+
+
+def test_inflate_reference_truncated_record(ctx):
+    """Interop with the reference's defect: its 65 535-byte truncated payload inflates to 65 513 bytes."""
+    r = corpus.gen_random(CHUNK, 596, 1).tobytes()
+    c = O.ref_deflate_chunk(r)
+    assert len(c) == CHUNK
+    out, rl, st = ctx.inflate_batch(c, [0], [len(c)], [0, 70000])
+    assert int(rl[0]) == 65513 and int(st[0]) == O.STREAM_TRUNCATED and out[:65513].tobytes() == r[:65513]
+
+
+@pytest.mark.parametrize("name", ["edge_r1", "edge_r2", "foreign"])
+def test_inflate_golden_reference_archives(ctx, name, is_gpu):
+    """Criterion (2): archives written by the unmodified reference binary inflate to the bytes the reference's own
+    decompress wrote (tests/golden/manifest.json)."""
+    man = json.load(open(os.path.join(GOLD, "manifest.json")))
+    recs = []
+    for arch in man[name]["archives"]:
+        recs += zwz_format.parse(open(os.path.join(GOLD, name, arch), "rb").read())
+    if not is_gpu:  # keep the emulated run short: whole files, smallest first, up to ~20 records
+        by = {}
+        for r in recs:
+            by.setdefault(r.path, []).append(r)
+        keep, cnt = [], 0
+        for p in sorted(by, key=lambda p: sum(len(r.payload) for r in by[p])):
+            if cnt + len(by[p]) > 20 or (name == "foreign" and p == "big/million.txt"):
+                continue
+            keep += by[p]
+            cnt += len(by[p])
+        recs = keep
+    comp, off = _cat([r.payload for r in recs])
+    cap = 1 << 20 if name == "foreign" else 65536
+    raw_off = np.arange(len(recs) + 1, dtype=np.uint64) * np.uint64(cap)
+    out, rl, st = ctx.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
+    files = {}
+    for i, r in enumerate(recs):
+        assert int(rl[i]) <= cap
+        files.setdefault(r.path, {})[r.seq] = out[int(raw_off[i]):int(raw_off[i]) + int(rl[i])].tobytes()
+    for path, parts in files.items():
+        data = b"".join(parts[s] for s in sorted(parts))
+        want = man[name]["outputs"][path]
+        assert (len(data), hashlib.md5(data).hexdigest()) == (want["size"], want["md5"]), path
+
+
+# ------------------------------------------------------------------------------------------------------------ deflate
+def _deflate_and_verify(ctx, chunks, level=0):
+    raw, off = _cat(chunks)
+    packed, poff, res = ctx.deflate_batch(raw, off[:-1], np.diff(off).astype(np.uint32), level)
+    sizes = []
+    for i, c in enumerate(chunks):
+        p = packed[int(poff[i]):int(poff[i + 1])].tobytes()
+        r = res[i]
+        assert int(r["len0"]) + int(r["len1"]) == len(p)
+        assert int(r["len0"]) <= CHUNK and int(r["len1"]) <= CHUNK  # the reader's payload array (decompression.cpp:116)
+        s0, s1 = p[:int(r["len0"])], p[int(r["len0"]):]
+        # criterion (1): the reference's zlib reaches Z_STREAM_END on every stream and returns the original bytes
+        d0 = zlib.decompressobj()
+        a = d0.decompress(s0)
+        assert d0.eof and not d0.unused_data
+        assert O.inflate(s0, 70000)[:2] == (a, O.STREAM_END)
+        assert O.ref_inflate_chunk(s0) == a
+        if r["len1"]:
+            d1 = zlib.decompressobj()
+            b = d1.decompress(s1)
+            assert d1.eof and not d1.unused_data
+            assert len(a) == int(r["raw0"])
+            a += b
+        else:
+            assert int(r["raw0"]) == len(c)
+        assert a == c, i
+        sizes.append(len(p))
+    return sizes, res
+
+
+def test_deflate_edge_cases(ctx):
+    t = corpus.gen_text(70000, 596, 11).tobytes()
+    chunks = [b"", b"a", b"ab", b"abc", b"abcd", b"aaaa", b"a" * 258, b"a" * 259, b"a" * 1000, b"ab" * 500, t[:96], t[:4096], bytes(range(256)) * 4,
+              b"\x00" * 20000]
+    sizes, res = _deflate_and_verify(ctx, chunks)
+    assert sizes[0] == 8  # empty chunk: 78 9c 03 00 00 00 00 01, exactly what the reference's zlib emits
+    for c, s in zip(chunks, sizes):
+        assert s <= len(zlib.compress(c, 6)) * 1.10 + 4, (len(c), s)
+
+
+def test_deflate_full_chunks_and_split_rule(ctx, is_gpu):
+    r = corpus.gen_random(CHUNK, 596, 21).tobytes()
+    chunks = [r, r[:65525], r[:65524], r[:65000], corpus.gen_text(CHUNK, 596, 22).tobytes()]
+    if is_gpu:
+        chunks += [corpus.gen_struct(CHUNK, 596, 23).tobytes(), corpus.gen_bitmap_like(CHUNK, 596, 24).tobytes(), b"\x00" * CHUNK,
+                   (b"0123456789abcdef" * 4096)[:CHUNK]]
+    sizes, res = _deflate_and_verify(ctx, chunks)
+    # incompressible chunks whose stored form would not fit 65 535 bytes come back as TWO streams (lossless, unlike the
+    # reference's silent truncation)
+    assert int(res[0]["len1"]) > 0 and int(res[0]["raw0"]) == 32768
+    assert int(res[1]["len1"]) > 0
+    assert int(res[2]["len1"]) == 0 and sizes[2] == 65524 + 11
+    assert int(res[3]["len1"]) == 0
+
+
+def test_deflate_ratio_within_tolerance_of_zlib6(ctx, is_gpu):
+    """Criterion (4): per content class, total size <= 1.03 x zlib level 6 on the same 65 535-byte chunking."""
+    n_chunks = 2 if not is_gpu else 24
+    size = 30000 if not is_gpu else CHUNK
+    for cls in "TSBJR":
+        chunks = [corpus.gen_file(cls, size, 596, 1000 + k).tobytes() for k in range(n_chunks)]
+        sizes, _ = _deflate_and_verify(ctx, chunks)
+        z = sum(O.ref_deflate_size(c) for c in chunks)
+        assert sum(sizes) <= RATIO_TOLERANCE * z, (cls, sum(sizes), z)
+
+
+def test_deflate_levels(ctx):
+    t = corpus.gen_text(20000, 596, 31).tobytes()
+    prev = None
+    for level in (1, 6, 9):
+        sizes, _ = _deflate_and_verify(ctx, [t], level)
+        if prev is not None:
+            assert sizes[0] <= prev * 1.01
+        prev = sizes[0]
+
+
+def test_deflate_unaligned_offsets(ctx):
+    base = corpus.gen_text(40000, 596, 41).tobytes()
+    chunks = [base[k:k + 3000 + k] for k in range(1, 18)]
+    _deflate_and_verify(ctx, chunks)
+
+
+def test_deflate_inflate_roundtrip_device_resident(ctx, is_gpu):
+    """deflate -> inflate entirely through the *_device entry points (data stays in HBM), then MD5 on the device."""
+    nfiles = 40 if not is_gpu else 4000
+    buf, offs, sizes = corpus.c2_buffer(nfiles, seed=597)
+    if not is_gpu:
+        offs = offs[:13]
+        buf = buf[:int(offs[-1])]
+    import zwz_b200
+    coff, clen, cfile, cseq = zwz_b200.chunk_table(offs)
+    slots = zwz_b200.deflate_bound(clen)
+    slot_off = np.zeros(len(clen) + 1, dtype=np.uint64)
+    np.cumsum(slots, out=slot_off[1:])
+    d_raw = ctx.malloc_device(buf.nbytes + 64)
+    d_out = ctx.malloc_device(int(slot_off[-1]) + 64)
+    d_back = ctx.malloc_device(buf.nbytes + 64)
+    try:
+        ctx.h2d(d_raw, buf)
+        res = ctx.deflate_batch_device(d_raw, coff, clen, d_out, slot_off[:-1])
+        assert (res["len1"] == 0).all()  # C2 files are single sub-65 535-byte chunks
+        rl, st = ctx.inflate_batch_device(d_out, slot_off[:-1], res["len0"], d_back, np.concatenate([coff, [np.uint64(offs[-1])]]))
+        assert (st == O.STREAM_END).all() and (rl == clen).all()
+        back = np.empty_like(buf)
+        ctx.d2h(back, d_back)
+        assert np.array_equal(back, buf)
+        dg = ctx.md5_batch_device(d_back, offs[:-1].astype(np.uint64), np.diff(offs).astype(np.uint64))
+        for i in range(0, len(offs) - 1, max(1, (len(offs) - 1) // 50)):
+            assert bytes(dg[i]).hex() == hashlib.md5(buf[int(offs[i]):int(offs[i + 1])].tobytes()).hexdigest()
+    finally:
+        for p in (d_raw, d_out, d_back):
+            ctx.free_device(p)
