@@ -120,32 +120,31 @@ ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, ui
     __syncwarp();
     // 4. leaf depths (walk to the root), histogram clamped at maxbits
     const uint32_t root = 2u * nused - 2u;
-    uint32_t overflow = 0;
     for (uint32_t i = lane; i < nused; i += 32u) {
         uint32_t d = 0, v = i;
         while (v != root) {
             v = S.parent[v];
             ++d;
         }
-        if (d > maxbits) {
-            d = maxbits;
-            ++overflow;
-        }
+        if (d > maxbits) d = maxbits;
         atomicAdd(&S.bl_count[d], 1u);
     }
-    overflow = warp_sum(overflow);
     __syncwarp();
-    // 5. zlib gen_bitlen repair: move leaves up until the Kraft sum fits
-    if (overflow && lane == 0) {
-        int ov = (int) overflow;
-        do {
+    // 5. repair after clamping (the step of zlib's gen_bitlen): the clamped lengths over-subscribe the code space by
+    //    `excess` units of 2^-maxbits; each step turns a leaf at the deepest level below maxbits into an internal node
+    //    whose children are that leaf and one of the clamped leaves, which frees exactly one unit.
+    if (lane == 0) {
+        uint32_t total = 0;
+        for (uint32_t b = 1; b <= maxbits; ++b) total += S.bl_count[b] << (maxbits - b);
+        int excess = (int) total - (int) (1u << maxbits);
+        while (excess > 0) {
             uint32_t bits = maxbits - 1u;
             while (S.bl_count[bits] == 0u) --bits;
             S.bl_count[bits]--;
             S.bl_count[bits + 1u] += 2u;
             S.bl_count[maxbits]--;
-            ov -= 2;
-        } while (ov > 0);
+            --excess;
+        }
     }
     __syncwarp();
     // 6. lengths by rank: the rarest symbols take the longest codes

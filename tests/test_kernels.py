@@ -238,6 +238,43 @@ def test_deflate_ratio_within_tolerance_of_zlib6(ctx, is_gpu):
         assert sum(sizes) <= RATIO_TOLERANCE * z, (cls, sum(sizes), z)
 
 
+def test_deflate_length_limited_codes(ctx):
+    """Fibonacci-like symbol frequencies push the unrestricted Huffman depth past 15 bits (and the code-length code past
+    7): the length-limiting repair has to leave a complete, decodable code."""
+    rng = np.random.Generator(np.random.Philox(key=[596, 4]))
+    chunks = []
+    for top in (18, 22, 24):
+        fib = [1, 1]
+        while len(fib) < top:
+            fib.append(fib[-1] + fib[-2])
+        scale = max(1, sum(fib) // 60000 + 1)
+        data = np.concatenate([np.full(max(1, f // scale), i, dtype=np.uint8) for i, f in enumerate(fib)])
+        rng.shuffle(data)
+        chunks.append(data[:CHUNK].tobytes())
+    # many distinct code lengths in the header stress the 7-bit code-length code
+    lens = np.concatenate([np.full(1 << k, 40 + k, dtype=np.uint8) for k in range(14)])
+    rng.shuffle(lens)
+    chunks.append(lens.tobytes())
+    _deflate_and_verify(ctx, chunks)
+
+
+def test_deflate_many_small_chunks(ctx, is_gpu):
+    """C2-shaped stress: every stream must decode under the reference's zlib (this is the test that caught an
+    over-subscribed code-length code)."""
+    nfiles = 250 if not is_gpu else 20000
+    sizes = corpus.c2_sizes(50000, 596)
+    want = sizes[np.argsort(-sizes, kind="stable")][30000:30000 + nfiles]
+    buf, _, _ = corpus.c2_buffer(nfiles + 200, 596)
+    foffs = np.zeros(nfiles + 1, dtype=np.int64)
+    np.cumsum(want, out=foffs[1:])
+    buf = buf[:int(foffs[-1])]
+    off = foffs[:-1].astype(np.uint64)
+    packed, poff, res = ctx.deflate_batch(buf, off, want.astype(np.uint32))
+    assert (res["len1"] == 0).all()
+    for i in range(nfiles):
+        assert zlib.decompress(packed[int(poff[i]):int(poff[i + 1])].tobytes()) == buf[int(foffs[i]):int(foffs[i + 1])].tobytes(), i
+
+
 def test_deflate_levels(ctx):
     t = corpus.gen_text(20000, 596, 31).tobytes()
     prev = None
