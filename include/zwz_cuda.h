@@ -144,6 +144,25 @@ int zwz_md5_final_device(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_tail, c
 /* verification.cpp:24-27: 16 digest bytes -> 32 lowercase hex characters (no terminator). */
 void zwz_md5_hex(const uint8_t digest[16], char hex[32]);
 
+/* ---- whole-batch passes used by the C++ host (one upload, one download per batch) -------------------------------------- */
+/* Chunks a batch of whole files exactly like the reference's producer (compression.cpp:52-64: floor(S/65535)+1 chunks per
+ * file, the last one S mod 65535 bytes, possibly empty). */
+uint64_t zwz_count_chunks(const uint64_t *file_off /* nf+1 */, uint32_t nf);
+/* Compress side of one batch: file i is data[file_off[i] .. file_off[i+1]). Uploads the span once, deflates every chunk,
+ * MD5s every file (md5_of_file(src), compression.cpp:95-103; pass digest = NULL to skip), packs and downloads the streams.
+ * Chunks come out in file order then sequence order; packed_off has zwz_count_chunks()+1 entries, res one per chunk. */
+int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                       uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest /* nf*16 or NULL */);
+/* Decompress side of one batch: record i is comp[off[i] .. off[i]+len[i]); records are given in OUTPUT order (all records
+ * of file 0 in sequence order, then file 1, ...), rec_file[i] = file index (non-decreasing), rec_cap[i] = capacity to give
+ * record i (65 535 is enough for every record the reference or this library writes; a record that needs more comes back with
+ * status ZWZ_STREAM_OUTPUT_FULL and raw_len = the size needed, and NOTHING is written to files_out — retry with larger caps).
+ * On success the records' bytes are concatenated per file into files_out (file_off_out[nf+1] filled by the call) and digest
+ * receives the MD5 of every file (md5_of_file(output), decompression.cpp:136; NULL to skip). */
+int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                           const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
+                           uint32_t *raw_len, uint32_t *status, uint8_t *digest /* nf*16 or NULL */, uint32_t flags);
+
 /* ---- Adler-32 (the zlib trailer; exported for tests) ---------------------------------------------------------------- */
 int zwz_adler32_batch_device(zwz_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint32_t *len, uint32_t n,
                              uint32_t *adler /* host, n */, void *stream);

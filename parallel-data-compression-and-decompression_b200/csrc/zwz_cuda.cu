@@ -46,6 +46,24 @@ ZWZ_KERNEL adler32_kernel(const uint8_t *__restrict__ data, const uint64_t *__re
     if (lane_id() == 0) adler[c] = a;
 }
 
+// concatenation of inflated records into contiguous files: one warp per record
+ZWZ_KERNEL gather_records_kernel(const uint8_t *__restrict__ slots, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ dst_off,
+                                 const uint32_t *__restrict__ len, uint8_t *dst, uint32_t n) {
+    uint32_t c = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (c >= n) return;
+    const uint8_t *s = slots + src_off[c];
+    uint8_t *d = dst + dst_off[c];
+    uint32_t bytes = len[c];
+    unsigned lane = lane_id();
+    if (((((uintptr_t) d) | ((uintptr_t) s)) & 15u) == 0u) {
+        uint32_t nv = bytes >> 4;
+        for (uint32_t i = lane; i < nv; i += 32u) ((uint4 *) d)[i] = ((const uint4 *) s)[i];
+        for (uint32_t i = (nv << 4) + lane; i < bytes; i += 32u) d[i] = s[i];
+    } else {
+        for (uint32_t i = lane; i < bytes; i += 32u) d[i] = s[i];
+    }
+}
+
 struct Arena {
     void *p = nullptr;
     size_t cap = 0;
@@ -383,8 +401,12 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
     return ZWZ_OK;
 }
 
-int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
-                      uint64_t *packed_off, zwz_deflate_result *res, int level) {
+static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
+                      uint32_t n, uint8_t *digest, int finalize, void *stream_v);
+
+static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
+                             uint64_t *packed_off, zwz_deflate_result *res, int level, const uint64_t *md5_off, const uint64_t *md5_len,
+                             uint32_t md5_n, uint8_t *digest) {
     if (!ctx) return ZWZ_E_ARG;
     if (!packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
     packed_off[0] = 0;
@@ -409,6 +431,11 @@ int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, con
     if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
     if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
     if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, raw + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "raw upload failed");
+    if (digest && md5_n) { // MD5 of the source files from the same resident copy (no second upload)
+        std::vector<uint64_t> mo(md5_n);
+        for (uint32_t i = 0; i < md5_n; ++i) mo[i] = md5_off[i] - lo;
+        if ((rc = md5_launch(ctx, nullptr, (const uint8_t *) ctx->bulk_in.p, mo.data(), md5_len, nullptr, md5_n, digest, 1, nullptr))) return rc;
+    }
     if ((rc = zwz_deflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, roff.data(), len, n, (uint8_t *) ctx->bulk_out.p, slot.data(), res,
                                        level, nullptr)))
         return rc;
@@ -465,6 +492,41 @@ int zwz_pack_streams_device(zwz_ctx *ctx, const uint8_t *d_slots, const uint64_t
     if ((rc = check_launch(ctx, "pack_streams_kernel"))) return rc;
     if (zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "pack kernel failed");
     return ZWZ_OK;
+}
+
+int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
+                      uint64_t *packed_off, zwz_deflate_result *res, int level) {
+    return deflate_host_impl(ctx, raw, off, len, n, out, out_cap, packed_off, res, level, nullptr, nullptr, 0, nullptr);
+}
+
+uint64_t zwz_count_chunks(const uint64_t *file_off, uint32_t nf) {
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < nf; ++i) c += (file_off[i + 1] - file_off[i]) / ZWZ_CHUNK_SIZE + 1;
+    return c;
+}
+
+int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                       uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!file_off || !packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
+    uint64_t nc = zwz_count_chunks(file_off, nf);
+    if (nc > 0xffffffffull) return fail(ctx, ZWZ_E_ARG, "too many chunks in one batch");
+    std::vector<uint64_t> coff((size_t) nc), flen(nf);
+    std::vector<uint32_t> clen((size_t) nc);
+    size_t k = 0;
+    for (uint32_t i = 0; i < nf; ++i) { // compression.cpp:52-64
+        uint64_t S = file_off[i + 1] - file_off[i];
+        flen[i] = S;
+        for (uint64_t o = 0;; o += ZWZ_CHUNK_SIZE) {
+            uint64_t left = S - o;
+            coff[k] = file_off[i] + o;
+            clen[k] = (uint32_t) (left < ZWZ_CHUNK_SIZE ? left : ZWZ_CHUNK_SIZE);
+            ++k;
+            if (left < ZWZ_CHUNK_SIZE) break;
+        }
+    }
+    return deflate_host_impl(ctx, data, coff.data(), clen.data(), (uint32_t) nc, out, out_cap, packed_off, res, level, file_off, flen.data(),
+                             digest ? nf : 0, digest);
 }
 
 // ======================================================================================================================
@@ -525,6 +587,97 @@ int zwz_inflate_batch(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, co
                                        status, flags, nullptr)))
         return rc;
     if (zwz_rt::memcpy_d2h(raw_out + raw_off[0], ctx->bulk_out.p, (size_t) roff[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
+        return fail(ctx, ZWZ_E_CUDA, "raw download failed");
+    return ZWZ_OK;
+}
+
+int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                           const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
+                           uint32_t *raw_len, uint32_t *status, uint8_t *digest, uint32_t flags) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (!file_off_out) return fail(ctx, ZWZ_E_ARG, "null argument");
+    for (uint32_t f = 0; f <= nf; ++f) file_off_out[f] = 0;
+    if (n == 0) {
+        if (digest && nf) { // every file is empty
+            std::vector<uint64_t> z(nf, 0);
+            int rc0 = reserve(ctx, ctx->bulk_in, 64, false);
+            if (rc0) return rc0;
+            return md5_launch(ctx, nullptr, (const uint8_t *) ctx->bulk_in.p, z.data(), z.data(), nullptr, nf, digest, 1, nullptr);
+        }
+        return ZWZ_OK;
+    }
+    if (!off || !len || !rec_cap || !rec_file || !raw_len || !status) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+        if (rec_file[i] >= nf || (i && rec_file[i] < rec_file[i - 1])) return fail(ctx, ZWZ_E_ARG, "rec_file must be non-decreasing and < nf");
+    }
+    std::vector<uint64_t> coff(n), slot(n + 1);
+    slot[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        coff[i] = off[i] - lo;
+        slot[i + 1] = slot[i] + (((uint64_t) rec_cap[i] + 15u) & ~15ull);
+    }
+    int rc;
+    if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
+    if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
+    if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, comp + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "compressed upload failed");
+    // per-record capacity is rec_cap, but slots are 16-byte aligned so the gather can use 128-bit copies
+    std::vector<uint64_t> cap_off(n + 1);
+    for (uint32_t i = 0; i <= n; ++i) cap_off[i] = slot[i];
+    // inflate_kernel takes capacity = raw_off[i+1]-raw_off[i]; the up-to-15 padding bytes per slot are harmless extra room,
+    // but OUTPUT_FULL must be judged against rec_cap — checked below.
+    if ((rc = zwz_inflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, coff.data(), len, n, (uint8_t *) ctx->bulk_out.p, cap_off.data(),
+                                       raw_len, status, flags, nullptr)))
+        return rc;
+    bool retry = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (status[i] == ZWZ_STREAM_OUTPUT_FULL || raw_len[i] > rec_cap[i]) {
+            if (raw_len[i] > rec_cap[i]) {
+                status[i] = ZWZ_STREAM_OUTPUT_FULL;
+                retry = true;
+            }
+        }
+    }
+    if (retry) return ZWZ_OK; // caller inspects status/raw_len and calls again with larger capacities
+    // layout of the concatenated files
+    std::vector<uint64_t> dst(n);
+    uint64_t acc = 0;
+    uint32_t f = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        while (f < rec_file[i]) file_off_out[++f] = acc;
+        dst[i] = acc;
+        acc += raw_len[i];
+    }
+    while (f < nf) file_off_out[++f] = acc;
+    if (acc > out_cap) return fail(ctx, ZWZ_E_CAPACITY, "output buffer too small");
+    const size_t m_dst = (size_t) n * 8, m_len = 2 * (size_t) n * 8, meta_bytes = m_len + (size_t) n * 4;
+    if ((rc = reserve(ctx, ctx->packed, (size_t) acc + align_up(meta_bytes, 256) + 256, false))) return rc;
+    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    memcpy(hp, slot.data(), (size_t) n * 8);
+    memcpy(hp + m_dst, dst.data(), (size_t) n * 8);
+    memcpy(hp + m_len, raw_len, (size_t) n * 4);
+    uint8_t *dmeta = (uint8_t *) ctx->packed.p;
+    uint8_t *d_files = dmeta + align_up(meta_bytes, 256);
+    if (zwz_rt::memcpy_h2d(dmeta, hp, meta_bytes, ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
+    {
+        ProfSpan ps(ctx, ZWZ_PROF_PACK, ctx->stream);
+        ZWZ_LAUNCH(zwz::gather_records_kernel, (n + 7) / 8, 256, 0, ctx->stream, (const uint8_t *) ctx->bulk_out.p, (const uint64_t *) dmeta,
+                   (const uint64_t *) (dmeta + m_dst), (const uint32_t *) (dmeta + m_len), d_files, n);
+    }
+    if ((rc = check_launch(ctx, "gather_records_kernel"))) return rc;
+    if (digest && nf) {
+        std::vector<uint64_t> fo(nf), fl(nf);
+        for (uint32_t i = 0; i < nf; ++i) {
+            fo[i] = file_off_out[i];
+            fl[i] = file_off_out[i + 1] - file_off_out[i];
+        }
+        if ((rc = md5_launch(ctx, nullptr, d_files, fo.data(), fl.data(), nullptr, nf, digest, 1, nullptr))) return rc;
+    }
+    if (zwz_rt::memcpy_d2h(files_out, d_files, (size_t) acc, ctx->stream) || zwz_rt::stream_sync(ctx->stream))
         return fail(ctx, ZWZ_E_CUDA, "raw download failed");
     return ZWZ_OK;
 }

@@ -1,0 +1,90 @@
+// distribute.cpp — work distribution: walk, size-descending sort, record file (file_sort.cpp:14-43, file_tools.cpp:6-23).
+//
+// The deal itself (rank r takes sorted files r, r+P, ...; compression.cpp:31-41) is the multi-GPU sharding rule of this
+// build: GPU index in place of MPI rank, no payload ever crosses GPUs.
+#include "zwz_host.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+namespace zwzhost {
+
+namespace fs = std::filesystem;
+
+RunConfig &config() {
+    static RunConfig c;
+    return c;
+}
+RunStats &stats() {
+    static RunStats s;
+    return s;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// The reference learns rank/size from MPI (main.cpp:12-13). Without MPI the launcher's environment carries them:
+// ZWZ_RANK/ZWZ_WORLD (ours), Open MPI / PMI / torchrun variables are accepted too, so `mpirun -n P main ...` keeps working
+// wherever an MPI launcher exists.
+void config_from_env() {
+    RunConfig &c = config();
+    c.world_rank = env_int("ZWZ_RANK", env_int("OMPI_COMM_WORLD_RANK", env_int("PMI_RANK", env_int("RANK", 0))));
+    c.world_size = env_int("ZWZ_WORLD", env_int("OMPI_COMM_WORLD_SIZE", env_int("PMI_SIZE", env_int("WORLD_SIZE", 1))));
+    int ndev = zwz_device_count();
+    int local = env_int("ZWZ_LOCAL_RANK", env_int("OMPI_COMM_WORLD_LOCAL_RANK", env_int("LOCAL_RANK", c.world_rank)));
+    c.device = env_int("ZWZ_DEVICE", ndev > 0 ? local % ndev : 0);
+    c.level = env_int("ZWZ_LEVEL", 0);
+    c.verbose = env_int("ZWZ_VERBOSE", 0) != 0;
+    c.verify_all = env_int("ZWZ_VERIFY_ALL", 0) != 0;
+    int mb = env_int("ZWZ_BATCH_MB", 0);
+    if (mb > 0) c.batch_bytes = (std::size_t) mb << 20;
+}
+
+std::vector<FileEntry> collect_and_sort(const fs::path &path) {
+    std::vector<FileEntry> files;
+    // same iterator and the same relative-path spelling as file_sort.cpp:15-20
+    for (const auto &entry : fs::recursive_directory_iterator(path)) {
+        if (entry.is_regular_file()) files.push_back({fs::relative(entry.path(), path).string(), static_cast<off_t>(entry.file_size())});
+    }
+    // same comparator, same (unstable) algorithm as file_sort.cpp:30-31: ties land where libstdc++'s introsort puts them,
+    // so on one box the deal is identical to the reference's
+    std::sort(files.begin(), files.end(), [](const FileEntry &a, const FileEntry &b) { return a.size > b.size; });
+    return files;
+}
+
+std::string sort_files_by_size(const fs::path &path) {
+    std::vector<FileEntry> files = collect_and_sort(path);
+    auto output_filename = path.parent_path() / "sorted_files_by_size.txt"; // file_sort.cpp:33
+    std::ofstream file(output_filename);
+    if (file.is_open()) {
+        for (const auto &e : files) file << e.relpath << "\n";
+    }
+    return output_filename.string();
+}
+
+int count_non_empty_lines(const std::string &file_path) {
+    std::ifstream file(file_path);
+    if (!file.is_open()) {
+        std::cerr << "Error opening file: " << file_path << std::endl;
+        return -1;
+    }
+    std::string line;
+    int lines = 0;
+    while (std::getline(file, line)) {
+        bool blank = true;
+        for (unsigned char ch : line)
+            if (!std::isspace(ch)) {
+                blank = false;
+                break;
+            }
+        if (!blank) ++lines;
+    }
+    return lines;
+}
+
+} // namespace zwzhost

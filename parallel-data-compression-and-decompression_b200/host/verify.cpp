@@ -1,0 +1,82 @@
+// verify.cpp — md5_of_file (verification.cpp:6-30) on the GPU, and the process-wide zwz_ctx.
+#include "zwz_host.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+
+namespace zwzhost {
+
+// one context per device per process, created on first use. No GPU => hard error: this build has no CPU path.
+zwz_ctx *ctx_for(int device) {
+    static std::mutex mu;
+    static std::map<int, zwz_ctx *> all;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = all.find(device);
+    if (it != all.end()) return it->second;
+    zwz_ctx *c = nullptr;
+    int rc = zwz_init(device, &c);
+    if (rc != ZWZ_OK || !c) {
+        std::cerr << "zwz: cannot initialise CUDA device " << device << " (error " << rc << "); there is no CPU fallback" << std::endl;
+        throw std::runtime_error("zwz_init failed");
+    }
+    all[device] = c;
+    return c;
+}
+
+// Streams the file through the device in pieces (the reference streams 1 024-byte reads through MD5_Update,
+// verification.cpp:15-19; the update granularity does not change the digest). Returns "" if the file cannot be opened,
+// like the reference (verification.cpp:8-11).
+std::string md5_of_file_on(int device, const std::string &file_path) {
+    FILE *f = std::fopen(file_path.c_str(), "rb");
+    if (!f) {
+        std::cerr << "Cannot open file: " << file_path << std::endl;
+        return "";
+    }
+    zwz_ctx *ctx = ctx_for(device);
+    const size_t piece = (size_t) 64 << 20; // multiple of 64
+    void *pin = nullptr, *dev = nullptr;
+    if (zwz_malloc_pinned(ctx, piece, &pin) != ZWZ_OK || zwz_malloc_device(ctx, piece + 64, &dev) != ZWZ_OK) {
+        std::fclose(f);
+        throw std::runtime_error(std::string("zwz: staging allocation failed: ") + zwz_last_error(ctx));
+    }
+    uint32_t state[4];
+    zwz_md5_state_init(state, 1);
+    uint64_t total = 0;
+    uint8_t digest[16];
+    bool done = false;
+    while (!done) {
+        size_t got = std::fread(pin, 1, piece, f);
+        total += got;
+        uint64_t off = 0;
+        if (got == piece) {
+            uint64_t len = got;
+            if (zwz_memcpy_h2d(ctx, dev, pin, got) != ZWZ_OK || zwz_md5_update_device(ctx, state, (const uint8_t *) dev, &off, &len, 1, nullptr) != ZWZ_OK)
+                throw std::runtime_error(std::string("zwz: md5 update failed: ") + zwz_last_error(ctx));
+        } else {
+            uint64_t full = got & ~(uint64_t) 63, tail = got - full;
+            if (got && zwz_memcpy_h2d(ctx, dev, pin, got) != ZWZ_OK) throw std::runtime_error("zwz: h2d failed");
+            if (full && zwz_md5_update_device(ctx, state, (const uint8_t *) dev, &off, &full, 1, nullptr) != ZWZ_OK)
+                throw std::runtime_error(std::string("zwz: md5 update failed: ") + zwz_last_error(ctx));
+            if (zwz_md5_final_device(ctx, state, (const uint8_t *) dev, &full, &tail, &total, 1, digest, nullptr) != ZWZ_OK)
+                throw std::runtime_error(std::string("zwz: md5 final failed: ") + zwz_last_error(ctx));
+            done = true;
+        }
+    }
+    std::fclose(f);
+    zwz_free_pinned(ctx, pin);
+    zwz_free_device(ctx, dev);
+    char hex[33];
+    zwz_md5_hex(digest, hex);
+    hex[32] = 0;
+    return std::string(hex, 32);
+}
+
+std::string md5_of_file(const std::string &file_path) { return md5_of_file_on(config().device, file_path); }
+
+bool is_md5_match(const std::string &file_path, const std::string &expected_md5) { return md5_of_file(file_path) == expected_md5; }
+
+} // namespace zwzhost

@@ -1,0 +1,188 @@
+"""The C++ host (`main compress|decompress <src> <dst>`) against the UNMODIFIED reference binary (oracle/_ref/main_ref).
+
+`[emu]`: the host sources linked against the SIMT-emulator build of the C ABI (CPU, here). `[cuda]`: the shipped `main`
+over libzwz_cuda.so on the B200. Criteria from BASELINE.json:
+  (1) the reference decompresses OUR archives to the original bytes, "MD5 match" on every file;
+  (2) WE decompress the REFERENCE's archives to bytes identical to the reference's own decompression (including the short
+      output of its truncated records) and print the same verdicts;
+  (3) the MD5 stored in our records is the reference's (OpenSSL) digest of the source file;
+  and the `.zwz` layout / archive naming / size-descending round-robin deal are the reference's.
+"""
+import filecmp
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import zwz_format
+from tools import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAIN_REF = os.path.join(ROOT, "oracle", "_ref", "main_ref")
+GOLD = os.path.join(ROOT, "tests", "golden")
+HOST = os.path.join(ROOT, "parallel-data-compression-and-decompression_b200", "host")
+
+needs_ref = pytest.mark.skipif(not os.path.exists(MAIN_REF), reason="oracle/_ref/main_ref not built (needs /root/reference once)")
+
+
+@pytest.fixture(params=[pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def main_bin(request):
+    if request.param == "emu":
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "simt"), "hostemu/main"], check=True, capture_output=True,
+                       env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+        return os.path.join(ROOT, "tests", "simt", "hostemu", "main")
+    p = os.path.join(HOST, "main")
+    assert os.path.exists(p), "build the host first (__graft_entry__.build())"
+    return p
+
+
+def run(cmd, env=None, check=True):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, env=e, capture_output=True, text=True)
+    if check:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout + r.stderr
+
+
+def same_tree(a, b):
+    c = filecmp.dircmp(a, b)
+    stack = [c]
+    while stack:
+        d = stack.pop()
+        assert not d.left_only and not d.right_only, (d.left_only, d.right_only)
+        for f in d.common_files:
+            assert filecmp.cmp(os.path.join(d.left, f), os.path.join(d.right, f), shallow=False), f
+        stack += list(d.subdirs.values())
+
+
+@pytest.fixture
+def edge_tree(tmp_path):
+    src = tmp_path / "work" / "edge"
+    src.mkdir(parents=True)
+    specs = corpus.edge_case_tree(str(src))
+    return str(src), specs
+
+
+@needs_ref
+def test_reference_decompresses_our_archive(main_bin, edge_tree, tmp_path):
+    src, specs = edge_tree
+    arch = str(tmp_path / "arch")
+    log = run([main_bin, "compress", src, arch])
+    assert "Operation: compress" in log and "Processor Count: 1" in log and "Time Taken:" in log
+    assert os.listdir(arch) == ["compressed_0.zwz"]                       # compression.cpp:151-159
+    assert os.path.exists(os.path.join(os.path.dirname(src), "sorted_files_by_size.txt"))  # file_sort.cpp:33
+    out = str(tmp_path / "out")
+    dlog = run([MAIN_REF, "decompress", arch, out])
+    assert dlog.count("MD5 match for file") == len(specs) and "MD5 mismatch" not in dlog
+    same_tree(src, out)  # lossless even for the incompressible 65 535-byte chunk the reference itself truncates
+
+
+@needs_ref
+def test_record_layout_and_md5(main_bin, edge_tree, tmp_path):
+    src, specs = edge_tree
+    arch = str(tmp_path / "arch")
+    run([main_bin, "compress", src, arch])
+    recs = zwz_format.parse(open(os.path.join(arch, "compressed_0.zwz"), "rb").read())
+    order = open(os.path.join(os.path.dirname(src), "sorted_files_by_size.txt")).read().split("\n")[:-1]
+    sizes = {s.relpath: s.size for s in specs}
+    assert [sizes[p] for p in order] == sorted(sizes.values(), reverse=True)          # size-descending
+    seen = []
+    by = {}
+    for r in recs:
+        if not seen or seen[-1] != r.path:
+            seen.append(r.path)
+        by.setdefault(r.path, []).append(r)
+    assert seen == order                                                              # records in file order, contiguous
+    for p, rs in by.items():
+        assert [r.seq for r in rs] == list(range(len(rs)))                            # 0..n-1
+        assert [r.last for r in rs] == [False] * (len(rs) - 1) + [True]
+        assert all(len(r.payload) <= 65535 for r in rs)                               # decompression.cpp:116
+        assert rs[-1].md5.decode() == hashlib.md5(open(os.path.join(src, p), "rb").read()).hexdigest()
+        assert len(rs) >= sizes[p] // 65535 + 1                                        # chunking rule (+1 per split chunk)
+    assert len(by["rand70k.bin"]) == 3                 # 65 535 incompressible -> split in two, + the 4 465-byte tail
+    assert len(by["exact65535.txt"]) == 2 and len(by["exact65535.txt"][1].payload) == 8   # empty tail chunk 78 9c 03 00 00 00 00 01
+    assert len(by["empty.bin"]) == 1
+
+
+@needs_ref
+def test_we_decompress_reference_archives_byte_exact(main_bin, edge_tree, tmp_path):
+    src, specs = edge_tree
+    arch = str(tmp_path / "arch_ref")
+    run([MAIN_REF, "compress", src, arch])
+    ref_out, our_out = str(tmp_path / "ref_out"), str(tmp_path / "our_out")
+    rlog = run([MAIN_REF, "decompress", arch, ref_out])
+    olog = run([main_bin, "decompress", arch, our_out])
+    same_tree(ref_out, our_out)
+    for key in ("MD5 match for file", "MD5 mismatch for file"):
+        assert rlog.count(key) == olog.count(key)
+    assert olog.count("MD5 mismatch for file") == 1   # the reference's own truncated record
+
+
+@pytest.mark.parametrize("name", ["edge_r1", "edge_r2", "foreign"])
+def test_we_decompress_golden_archives(main_bin, name, tmp_path):
+    """Same check against the committed archives (no reference binary needed at run time)."""
+    man = json.load(open(os.path.join(GOLD, "manifest.json")))
+    out = str(tmp_path / "out")
+    log = run([main_bin, "decompress", os.path.join(GOLD, name), out])
+    got = {}
+    for d, _, files in os.walk(out):
+        for f in files:
+            p = os.path.join(d, f)
+            b = open(p, "rb").read()
+            got[os.path.relpath(p, out)] = {"size": len(b), "md5": hashlib.md5(b).hexdigest()}
+    assert got == man[name]["outputs"]
+    assert log.count("MD5 match for file") == man[name]["verdicts"]["match"]
+    assert log.count("MD5 mismatch for file") == man[name]["verdicts"]["mismatch"]
+
+
+@needs_ref
+def test_two_ranks_same_deal_as_reference(main_bin, edge_tree, tmp_path):
+    """`mpirun -n 2` analogue: rank r takes sorted files r, r+2, ... and writes compressed_<r>.zwz (compression.cpp:31-41,157)."""
+    src, specs = edge_tree
+    ours, ref = str(tmp_path / "ours"), str(tmp_path / "ref")
+    bc = tmp_path / "bc"
+    bc.mkdir()
+    for r in (0, 1):
+        run([MAIN_REF, "compress", src, ref], {"ZWZ_STUB_SIZE": "2", "ZWZ_STUB_RANK": str(r), "ZWZ_STUB_DIR": str(bc)})
+    procs = [subprocess.Popen([main_bin, "compress", src, ours], env={**os.environ, "ZWZ_WORLD": "2", "ZWZ_RANK": str(r)},
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in (0, 1)]
+    for p in procs:
+        p.communicate()
+        assert p.returncode == 0
+    assert sorted(os.listdir(ours)) == sorted(os.listdir(ref)) == ["compressed_0.zwz", "compressed_1.zwz"]
+    for a in ("compressed_0.zwz", "compressed_1.zwz"):
+        po = [r.path for r in zwz_format.parse(open(os.path.join(ours, a), "rb").read()) if r.seq == 0]
+        pr = [r.path for r in zwz_format.parse(open(os.path.join(ref, a), "rb").read()) if r.seq == 0]
+        assert po == pr, a
+    out = str(tmp_path / "out")
+    dlog = run([MAIN_REF, "decompress", ours, out])
+    assert dlog.count("MD5 match for file") == len(specs)
+    same_tree(src, out)
+
+
+def test_self_round_trip_and_multi_batch(main_bin, tmp_path):
+    """Small batches force many GPU round trips and the large-file streaming path (segments + chained MD5)."""
+    src = tmp_path / "w" / "src"
+    src.mkdir(parents=True)
+    specs = corpus.c1_specs(12, seed=599, min_size=2000, max_size=300_000)
+    specs.append(corpus.FileSpec("big/huge.log", 4_400_000, "T", 999))   # > 64 chunks => segmented path with ZWZ_BATCH_MB=1
+    corpus.write_tree(str(src), specs, 599)
+    arch, out = str(tmp_path / "arch"), str(tmp_path / "out")
+    run([main_bin, "compress", str(src) + "/", arch + "/"], {"ZWZ_BATCH_MB": "1"})   # trailing slashes are stripped (main.cpp:72-76)
+    log = run([main_bin, "decompress", arch, out], {"ZWZ_BATCH_MB": "1"})
+    assert log.count("MD5 match for file") == len(specs) and "mismatch" not in log
+    same_tree(str(src), out)
+
+
+def test_usage_and_errors(main_bin, tmp_path):
+    r = subprocess.run([main_bin, "compress"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Usage:" in r.stderr
+    r = subprocess.run([main_bin, "compress", str(tmp_path / "nope"), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Source path does not exist." in r.stderr
+    (tmp_path / "s").mkdir()
+    r = subprocess.run([main_bin, "frobnicate", str(tmp_path / "s"), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Invalid operation" in r.stderr
