@@ -1,47 +1,63 @@
-// deflate_match.cuh — LZ77 match finding for one <= 65 535-byte chunk per CTA, everything in shared memory.
+// deflate_match.cuh — LZ77 match finding for <= 65 535-byte chunks, everything in shared memory.
 //
 // First half of the replacement for zlib's deflate() at compression.cpp:119-134 (the second half is deflate_encode.cuh).
 //
-// Per chunk (one persistent CTA of 1024 threads per SM, chunks handed out by an atomic counter):
+// Per chunk (persistent CTAs, chunks handed out by an atomic counter):
 //   1. the chunk is staged HBM -> shared memory with one bulk asynchronous copy (cp.async.bulk + mbarrier, SASS UBLKCP),
-//      16-byte aligned superset of the chunk, the chunk itself starts at byte `skew` of the staging buffer;
-//   2. warp 0 builds EXACT hash chains (3-byte hash, 14-bit head table, u16 prev[] per position) 32 positions per step:
-//      lanes with the same hash inside the step are linked with __match_any_sync, the lowest of a group links to the
-//      head table, the highest becomes the new head. The chain of position p is final as soon as the build front has
-//      passed p, which it publishes through a shared-memory counter;
-//   3. the other 31 warps (and warp 0 once it is done) pull 32-position tiles and, one lane per position, walk the
-//      chain: 4-byte compares on funnel-shifted aligned words, early reject on the bytes around the current best
-//      length, `depth` candidates at most, stop at `nice` bytes;
-//   4. the best (length, distance) of EVERY position goes to the chunk's scratch in HBM (4 bytes per input byte,
+//      a 16-byte aligned superset of the chunk; the chunk itself starts at byte `skew` of the staging buffer;
+//   2. all threads hash every position (3-byte multiplicative hash) into prev[] in parallel;
+//   3. warp 0 turns the hashes into EXACT hash chains, 32 positions per step: lanes with the same hash inside the step
+//      are linked with __match_any_sync, the lowest lane of a group links to the head table, the highest becomes the new
+//      head. Chains are final behind the build front, which is published through a shared-memory counter;
+//   4. the other warps (and warp 0 once it is done) pull 32-position tiles and, one lane per position, walk the chain:
+//      byte checks around the current best length reject most candidates, survivors are compared 4 bytes at a time on
+//      funnel-shifted aligned words; `depth` candidates at most, stop at `nice` bytes;
+//   5. the best (length, distance) of EVERY position goes to the chunk's scratch in HBM (4 bytes per input byte,
 //      coalesced); the parse in deflate_encode.cuh picks the path through them;
-//   5. Adler-32 of the chunk is reduced from shared memory while it is there.
+//   6. Adler-32 of the chunk is reduced from shared memory while it is there.
 //
-// Shared memory: 65 600 (chunk) + 131 072 (prev) + 32 768 (head) + control = 229 952 bytes -> one CTA per SM.
-// Algorithmic HBM bytes per chunk for the roofline: N_raw read (+ the 4 N_raw scratch write, which is traffic of this
-// design, not of the algorithm — reported separately in DESIGN.md).
+// Three size classes so that small chunks do not leave an SM to one serial chain builder (config C2 is 370 000 chunks of
+// ~6.7 KB): the class fixes the shared-memory footprint and with it how many CTAs — each with its own builder warp — an SM
+// holds.
+//      class   chunk bytes   threads   smem/CTA   CTAs/SM   hash bits
+//        S       <=  8 192      256     ~33 KB       6         12
+//        M       <= 32 768      512    ~113 KB       2         13
+//        L       <= 65 535     1024    ~225 KB       1         14
+// Algorithmic HBM bytes per chunk for the roofline: N_raw read (the 4 N_raw scratch write is traffic of this design, not of
+// the algorithm — reported separately in DESIGN.md).
 #pragma once
 #include "zwz_common.cuh"
 
 namespace zwz {
 
-#define ZWZ_DM_THREADS 1024
-#define ZWZ_DM_HBITS 14
 #define ZWZ_DM_NIL 0xffffu
-#define ZWZ_DM_DATA_BYTES 65600u
-#define ZWZ_DM_SMEM_BYTES (ZWZ_DM_DATA_BYTES + 131072u + (2u << ZWZ_DM_HBITS) + 512u)
+
+template <int CLS> struct MatchClass;
+template <> struct MatchClass<0> {
+    static constexpr uint32_t kCap = 8192, kThreads = 256, kHBits = 12, kData = 8192 + 64;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+};
+template <> struct MatchClass<1> {
+    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+};
+template <> struct MatchClass<2> {
+    static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+};
 
 struct MatchCtl {
     unsigned long long mbar;   // mbarrier for the bulk copy
     volatile uint32_t front;   // positions < front have final chains
     uint32_t next_tile;
-    uint32_t cur_chunk;
+    uint32_t cur_work;
     uint32_t pad;
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
 
-ZWZ_DEV uint32_t dm_hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
+template <int HBITS> ZWZ_DEV uint32_t dm_hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
     uint32_t v = b0 | (b1 << 8) | (b2 << 16);
-    return (v * 0x9E3779B1u) >> (32 - ZWZ_DM_HBITS);
+    return (v * 0x9E3779B1u) >> (32 - HBITS);
 }
 
 #ifndef ZWZ_EMU
@@ -69,12 +85,16 @@ ZWZ_DEV void dm_mbar_wait(unsigned long long *bar, uint32_t parity) {
 }
 #endif
 
-ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) {
+template <int CLS>
+ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJob job, const uint32_t *__restrict__ order, uint32_t n_work,
+                                                                         uint32_t *work_counter) {
+    constexpr uint32_t T = MatchClass<CLS>::kThreads, HB = MatchClass<CLS>::kHBits, DATA = MatchClass<CLS>::kData;
+    constexpr uint32_t NW = T / 32u;
     ZWZ_DYN_SMEM(smem);
-    uint32_t *dataw = (uint32_t *) smem;                                                    // chunk bytes as aligned words
-    uint16_t *prev = (uint16_t *) (smem + ZWZ_DM_DATA_BYTES);                               // [65536]
-    uint16_t *head = (uint16_t *) (smem + ZWZ_DM_DATA_BYTES + 131072u);                     // [1 << HBITS]
-    MatchCtl *ctl = (MatchCtl *) (smem + ZWZ_DM_DATA_BYTES + 131072u + (2u << ZWZ_DM_HBITS));
+    const uint32_t *dataw = (const uint32_t *) smem;                                  // chunk bytes as aligned words
+    uint16_t *prev = (uint16_t *) (smem + DATA);
+    uint16_t *head = (uint16_t *) (smem + DATA + MatchClass<CLS>::kPrevBytes);
+    MatchCtl *ctl = (MatchCtl *) (smem + DATA + MatchClass<CLS>::kPrevBytes + (2u << HB));
     const uint8_t *datab = (const uint8_t *) smem;
     const unsigned tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     uint32_t parity = 0;
@@ -85,10 +105,11 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) ctl->cur_chunk = atomicAdd(job.work_counter, 1u);
+        if (tid == 0) ctl->cur_work = atomicAdd(work_counter, 1u);
         __syncthreads();
-        const uint32_t c = ctl->cur_chunk;
-        if (c >= job.n) break;
+        const uint32_t w = ctl->cur_work;
+        if (w >= n_work) break;
+        const uint32_t c = order[w];
         const uint32_t n = job.raw_len[c];
         const uint8_t *src = job.raw + job.raw_off[c];
         const uint32_t skew = (uint32_t) ((uintptr_t) src & 15u);
@@ -98,9 +119,9 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
 #ifndef ZWZ_EMU
         if (tid == 0 && stage_bytes) dm_bulk_g2s(smem, src - skew, stage_bytes, &ctl->mbar);
 #else
-        for (uint32_t i = tid; i < skew + n; i += ZWZ_DM_THREADS) smem[i] = i < skew ? 0 : src[i - skew];
+        for (uint32_t i = tid; i < skew + n; i += T) smem[i] = i < skew ? 0 : src[i - skew];
 #endif
-        for (uint32_t i = tid; i < (1u << ZWZ_DM_HBITS) / 2u; i += ZWZ_DM_THREADS) ((uint32_t *) head)[i] = 0xffffffffu;
+        for (uint32_t i = tid; i < (1u << HB) / 2u; i += T) ((uint32_t *) head)[i] = 0xffffffffu;
         if (tid == 0) {
             ctl->front = 0;
             ctl->next_tile = 0;
@@ -119,16 +140,19 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
         const uint32_t nhash = n >= 3u ? n - 2u : 0u; // positions that own a 3-byte hash
         const uint32_t ntiles = (n + 31u) >> 5;
 
-        // ---- 2. warp 0: exact chain build ----
+        // ---- 2. hash every position (parallel); prev[p] holds hash(p) until the builder replaces it by the link ----
+        for (uint32_t p = tid; p < nhash; p += T) {
+            uint32_t v = ld32u(dataw, skew + p);
+            prev[p] = (uint16_t) dm_hash3<HB>(v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu);
+        }
+        __syncthreads();
+
+        // ---- 3. warp 0: exact chain build ----
         if (wid == 0) {
             for (uint32_t p0 = 0; p0 < nhash; p0 += 32u) {
                 uint32_t p = p0 + lane;
                 bool valid = p < nhash;
-                uint32_t h = 0x10000u + lane; // unique => singleton group
-                if (valid) {
-                    uint32_t a = skew + p;
-                    h = dm_hash3(datab[a], datab[a + 1], datab[a + 2]);
-                }
+                uint32_t h = valid ? (uint32_t) prev[p] : 0x10000u + lane; // out-of-range lanes form singleton groups
                 unsigned grp = __match_any_sync(ZWZ_FULL, h);
                 if (valid) {
                     unsigned lower = grp & ((1u << lane) - 1u);
@@ -137,15 +161,20 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
                 }
                 __syncwarp();
                 if (valid && (grp >> lane) == 1u) head[h] = (uint16_t) p;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) ctl->front = p0 + 32u;
+                if ((p0 & 96u) == 96u) { // publish every 4 steps
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) ctl->front = p0 + 32u;
+                } else {
+                    __syncwarp();
+                }
             }
             __threadfence_block();
+            __syncwarp();
             if (lane == 0) ctl->front = 0x7fffffffu;
         }
 
-        // ---- 3. search: one lane per position, 32-position tiles ----
+        // ---- 4. search: one lane per position, 32-position tiles ----
         for (;;) {
             uint32_t tile = 0;
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
@@ -161,16 +190,18 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
                 const uint32_t maxlen = (n - p) < ZWZ_MAX_MATCH ? (n - p) : ZWZ_MAX_MATCH;
                 const uint32_t limit = p > ZWZ_MAX_DIST ? p - ZWZ_MAX_DIST : 0u;
                 const uint32_t ap = skew + p;
+                const uint32_t first3 = ld32u(dataw, ap) & 0x00ffffffu;
+                uint32_t scan_end = datab[ap + 2u], scan_end1 = datab[ap + 1u]; // bytes at best_len and best_len - 1
                 uint32_t cand = prev[p];
                 uint32_t budget = job.depth;
                 while (cand != ZWZ_DM_NIL && cand >= limit && budget-- != 0u) {
                     const uint32_t ac = skew + cand;
-                    // early reject: the 4 bytes ending at index best_len must match for the candidate to be longer
-                    uint32_t o = (best_len < 3u ? 3u : best_len) - 3u;
-                    uint32_t x = ld32u(dataw, ac + o) ^ ld32u(dataw, ap + o);
-                    if (best_len < 3u) x &= 0x00ffffffu;
-                    if (x == 0u) {
-                        uint32_t len = 0;
+                    const uint32_t nxt = prev[cand]; // next link is fetched while this candidate is examined
+                    // cheap rejects first (zlib's longest_match order): the byte that would extend the best match, its
+                    // predecessor, then the 3-byte prefix (hash collisions)
+                    if (datab[ac + best_len] == scan_end && datab[ac + best_len - 1u] == scan_end1 &&
+                        (ld32u(dataw, ac) & 0x00ffffffu) == first3) {
+                        uint32_t len = 3u;
                         while (len < maxlen) {
                             uint32_t y = ld32u(dataw, ac + len) ^ ld32u(dataw, ap + len);
                             if (y) {
@@ -184,19 +215,21 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
                             best_len = len;
                             best_dist = p - cand;
                             if (len >= job.nice || len >= maxlen) break;
+                            scan_end = datab[ap + len];
+                            scan_end1 = datab[ap + len - 1u];
                         }
                     }
-                    cand = prev[cand];
+                    cand = nxt;
                 }
                 if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             }
-            if (p < n) mout[p] = best_len >= 3u ? ((best_len << 16) | best_dist) : 0u; // dist 32768 needs all 16 low bits
+            if (p < n) mout[p] = best_len >= 3u ? ((best_len << 16) | best_dist) : 0u;
         }
         __syncthreads();
 
-        // ---- 5. Adler-32 of the chunk ----
+        // ---- 6. Adler-32 of the chunk ----
         {
-            uint32_t seg = (n + ZWZ_DM_THREADS - 1u) / ZWZ_DM_THREADS;
+            uint32_t seg = (n + T - 1u) / T;
             uint32_t lo = tid * seg, hi = lo + seg;
             if (lo > n) lo = n;
             if (hi > n) hi = n;
@@ -223,9 +256,9 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_DM_THREADS, 1) lz_match_kernel(DeflateJob job) 
             }
             __syncthreads();
             if (wid == 0) {
-                part.a = ctl->adler_a[lane];
-                part.b = ctl->adler_b[lane];
-                part.len = ctl->adler_len[lane];
+                part.a = lane < NW ? ctl->adler_a[lane] : 0u;
+                part.b = lane < NW ? ctl->adler_b[lane] : 0u;
+                part.len = lane < NW ? ctl->adler_len[lane] : 0u;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     AdlerPart o;

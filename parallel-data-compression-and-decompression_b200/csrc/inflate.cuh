@@ -255,7 +255,9 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
         if (q_ >= pend_lo && q_ < pos && q_ < cap) out[q_] = (uint8_t) mybyte;   \
         pend_lo = pos;                                                           \
     } while (0)
-#define INF_NEED(nbits_) (infb_used(B) + (uint64_t) (nbits_) <= total_bits)
+// Everything already in `hold` is real stream data while fed <= total_bits; only the tail of a stream (or a truncated
+// one) needs the per-symbol availability checks that give zlib's exact stop position.
+#define INF_NEED(nbits_) (B.fed <= total_bits || infb_used(B) + (uint64_t) (nbits_) <= total_bits)
 
     // ---- RFC 1950 header (inflate.c HEAD) ----
     infb_refill(B);
@@ -427,10 +429,26 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
 
         // ---- symbol loop ----
         for (;;) {
-            infb_refill(B);
+            infb_refill(B); // >= 33 bits: room for two literal/length codes before the next refill
             uint32_t e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
             uint32_t kind = (e >> 8) & 3u;
             uint32_t nb = e & 15u;
+            if (kind == INF_KIND_LIT && INF_NEED(nb)) { // hot path: literal, then look at the next code right away
+                infb_drop(B, nb);
+                if (lane == (pos & 31u)) mybyte = e >> 16;
+                pos++;
+                if ((pos & 31u) == 0u) INF_FLUSH_LITS();
+                e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
+                kind = (e >> 8) & 3u;
+                nb = e & 15u;
+                if (kind == INF_KIND_LIT && INF_NEED(nb)) {
+                    infb_drop(B, nb);
+                    if (lane == (pos & 31u)) mybyte = e >> 16;
+                    pos++;
+                    if ((pos & 31u) == 0u) INF_FLUSH_LITS();
+                    continue;
+                }
+            }
             if (kind == INF_KIND_SPECIAL) {
                 if ((e >> 4) & 15u) { // code longer than the table index: canonical walk (complete sets only get here)
                     uint32_t len = 0;
@@ -456,7 +474,8 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
                 continue;
             }
             if (kind == INF_KIND_EOB) break;
-            // length
+            // length (the code may have been the second one since the last refill: top up before the extra bits)
+            infb_refill(B);
             uint32_t eb = (e >> 4) & 15u;
             uint32_t mlen = (e >> 16) + ((uint32_t) B.hold & ((1u << eb) - 1u));
             if (!INF_NEED(eb)) {
@@ -495,7 +514,7 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
             INF_FLUSH_LITS();
             __syncwarp();
             if (pos + mlen > cap) overflow = true;
-            if (dist >= 32u) {
+            if (dist >= 32u || dist >= mlen) {
                 for (uint32_t base = 0; base < mlen; base += 32u) { // warp-uniform trip count
                     uint32_t q = pos + base + lane;
                     if (base + lane < mlen && q < cap) out[q] = ((volatile uint8_t *) out)[q - dist];

@@ -81,6 +81,7 @@ struct zwz_ctx {
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, counter;
     size_t batch_raw_bytes = (size_t) 1 << 30; // raw bytes per internal deflate sub-batch (scratch = 4x that)
+    size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
     bool profiling = false;
     struct Span {
@@ -197,8 +198,10 @@ int zwz_init(int device, zwz_ctx **out) {
         return ZWZ_E_NODEVICE;
     }
 #endif
-    if (ctx->smem_optin < ZWZ_DM_SMEM_BYTES || zwz_rt::stream_create(&ctx->stream) ||
-        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel, ZWZ_DM_SMEM_BYTES)) {
+    if (ctx->smem_optin < zwz::MatchClass<2>::kSmem || zwz_rt::stream_create(&ctx->stream) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<0>, zwz::MatchClass<0>::kSmem) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<1>, zwz::MatchClass<1>::kSmem) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem)) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
@@ -319,18 +322,18 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
     }
     if (total_raw && !d_raw) return fail(ctx, ZWZ_E_ARG, "null raw buffer");
 
-    // descriptors: [raw_off u64][scr_off u64][out_off u64][raw_len u32] per chunk, then results + adler on the device
-    const size_t meta_bytes = (size_t) n * (8 + 8 + 8 + 4);
+    // descriptors: [raw_off u64][scr_off u64][out_off u64][raw_len u32][order u32] per chunk, then results + adler on the device
+    const size_t meta_bytes = (size_t) n * (8 + 8 + 8 + 4 + 4);
     const size_t dev_meta_bytes = align_up(meta_bytes, 256) + (size_t) n * 16 + (size_t) n * 4 + 256;
     int rc;
     if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 16), true))) return rc;
     if ((rc = reserve(ctx, ctx->meta, dev_meta_bytes, false))) return rc;
-    if ((rc = reserve(ctx, ctx->counter, 256, false))) return rc;
 
     uint64_t *h_raw_off = (uint64_t *) ctx->pin_meta.p;
     uint64_t *h_scr_off = h_raw_off + n;
     uint64_t *h_out_off = h_scr_off + n;
     uint32_t *h_len = (uint32_t *) (h_out_off + n);
+    uint32_t *h_order = h_len + n;
 
     // sub-batches bounded by scratch: scratch offsets restart at 0 in every sub-batch
     std::vector<uint32_t> sub_begin;
@@ -356,11 +359,33 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         sub_begin.push_back(n);
     }
     if ((rc = reserve(ctx, ctx->scratch, max_scr * 4 + 256, false))) return rc;
+    // size classes (deflate_match.cuh): per sub-batch, chunk indices grouped by class, longest first inside a class so the
+    // persistent CTAs end together
+    const size_t nsub = sub_begin.size() - 1;
+    std::vector<uint32_t> cls_begin(nsub * 4);
+    for (size_t s = 0; s < nsub; ++s) {
+        uint32_t b = sub_begin[s], e = sub_begin[s + 1];
+        uint32_t *o = h_order + b;
+        uint32_t k = 0;
+        for (int cls = 0; cls < 3; ++cls) {
+            cls_begin[s * 4 + cls] = k;
+            uint32_t lo_len = cls == 0 ? 0u : (cls == 1 ? 8193u : 32769u), hi_len = cls == 0 ? 8192u : (cls == 1 ? 32768u : 65535u);
+            uint32_t k0 = k;
+            for (uint32_t i = b; i < e; ++i)
+                if (len[i] >= lo_len && len[i] <= hi_len) o[k++] = i - b;
+            std::stable_sort(o + k0, o + k, [&](uint32_t x, uint32_t y) { return len[b + x] > len[b + y]; });
+        }
+        cls_begin[s * 4 + 3] = k;
+    }
+    if ((rc = reserve(ctx, ctx->counter, nsub * 16 + 256, false))) return rc;
+    if (zwz_rt::memset_device(ctx->counter.p, 0, nsub * 16, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
 
     uint8_t *dm = (uint8_t *) ctx->meta.p;
     if (zwz_rt::memcpy_h2d(dm, ctx->pin_meta.p, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint32_t *d_res = (uint32_t *) (dm + align_up(meta_bytes, 256));
     uint32_t *d_adler = d_res + (size_t) n * 4;
+    ctx->last_res_off = align_up(meta_bytes, 256);
+    ctx->last_slot_off = 2 * (size_t) n * 8;
 
     const LevelParams lp = level_params(level);
     for (size_t s = 0; s + 1 < sub_begin.size(); ++s) {
@@ -378,14 +403,30 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         job.n = e - b;
         job.depth = lp.depth;
         job.nice = lp.nice;
-        job.work_counter = (uint32_t *) ctx->counter.p;
-        if (zwz_rt::memset_device(ctx->counter.p, 0, 4, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
-        uint32_t grid1 = std::min<uint32_t>(job.n, (uint32_t) ctx->sm_count);
-        {
+        job.work_counter = nullptr;
+        const uint32_t *d_order = (const uint32_t *) ((const uint64_t *) dm + 3 * (size_t) n) + n + b;
+        uint32_t *d_counters = (uint32_t *) ctx->counter.p + s * 4;
+        for (int cls = 0; cls < 3; ++cls) {
+            uint32_t w0 = cls_begin[s * 4 + cls], w1 = cls_begin[s * 4 + cls + 1];
+            if (w1 == w0) continue;
             ProfSpan ps(ctx, ZWZ_PROF_MATCH, st);
-            ZWZ_LAUNCH(zwz::lz_match_kernel, grid1, ZWZ_DM_THREADS, ZWZ_DM_SMEM_BYTES, st, job);
+            if (cls == 0) {
+                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count * 6u);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<0>, grid, zwz::MatchClass<0>::kThreads, zwz::MatchClass<0>::kSmem, st, job, d_order + w0, w1 - w0,
+                           d_counters + cls);
+            } else if (cls == 1) {
+                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count * 2u);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<1>, grid, zwz::MatchClass<1>::kThreads, zwz::MatchClass<1>::kSmem, st, job, d_order + w0, w1 - w0,
+                           d_counters + cls);
+            } else {
+                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<2>, grid, zwz::MatchClass<2>::kThreads, zwz::MatchClass<2>::kSmem, st, job, d_order + w0, w1 - w0,
+                           d_counters + cls);
+            }
+            ctx->launches++;
         }
         if ((rc = check_launch(ctx, "lz_match_kernel"))) return rc;
+        ctx->launches--; // check_launch counted one more
         uint32_t grid2 = (job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS;
         {
             ProfSpan ps(ctx, ZWZ_PROF_ENCODE, st);
@@ -451,8 +492,8 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
     if (zwz_rt::memcpy_h2d(d_poff, ctx->pin_meta.p, pm, ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "offset upload failed");
     // slot offsets and results are still in ctx->meta from the call above
     const uint8_t *dm = (const uint8_t *) ctx->meta.p;
-    const uint64_t *d_slot_off = (const uint64_t *) dm + 2 * (size_t) n;
-    const uint32_t *d_res = (const uint32_t *) (dm + align_up((size_t) n * 28, 256));
+    const uint64_t *d_slot_off = (const uint64_t *) (dm + ctx->last_slot_off);
+    const uint32_t *d_res = (const uint32_t *) (dm + ctx->last_res_off);
     {
         ProfSpan ps(ctx, ZWZ_PROF_PACK, ctx->stream);
         ZWZ_LAUNCH(zwz::pack_streams_kernel, (n + 7) / 8, 256, 0, ctx->stream, (const uint8_t *) ctx->bulk_out.p, d_slot_off, d_res, d_packed,
