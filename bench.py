@@ -132,7 +132,7 @@ class ClockSampler:
 # CPU baseline: the reference's call sequences (oracle_ref_* in oracle/zwz_oracle.c: system zlib L6 deflate, zlib inflate,
 # OpenSSL MD5 in 1024-byte updates), fanned out over host threads (ctypes releases the GIL).
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_step(buf, foffs, coff, clen, threads):
+def cpu_step(buf, foffs, coff, clen, threads, do_md5=True):
     """One full step (compress side + decompress side) on the CPU. Returns (seconds, compressed_bytes)."""
     import ctypes as C
     from concurrent.futures import ThreadPoolExecutor
@@ -176,9 +176,11 @@ def cpu_step(buf, foffs, coff, clen, threads):
 
     t0 = time.perf_counter()
     run(deflate)
-    run(md5(buf, hex1))
+    if do_md5:
+        run(md5(buf, hex1))
     run(inflate)
-    run(md5(back, hex2))
+    if do_md5:
+        run(md5(back, hex2))
     dt = time.perf_counter() - t0
     ok = bool((raw_len == clen).all()) and np.array_equal(hex1, hex2)
     return dt, int(out_len.sum()), ok
@@ -216,12 +218,16 @@ def main():
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
+                    help="auto: on for c2/c1 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
+                         "the MD5 of ONE file is a single serial chain, one lane, ~0.1 GB/s)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
     if args.files == 0:
         args.files = {"c2": 370_000, "c3": 2 << 30, "c1": 2 << 30}[args.workload]
 
+    do_md5 = args.md5 == "on" or (args.md5 == "auto" and args.workload != "c3")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -238,7 +244,7 @@ def main():
         times = []
         comp = 0
         for i in range(args.warmup + args.steps):
-            dt, comp, ok = cpu_step(sb, so, coff, clen, cores)
+            dt, comp, ok = cpu_step(sb, so, coff, clen, cores, do_md5)
             assert ok or args.workload != "c2"
             if i >= args.warmup:
                 times.append(dt)
@@ -293,12 +299,12 @@ def main():
     def device_step():
         """inputs resident in HBM"""
         res = ctx.deflate_batch_device(d_raw.data_ptr(), coff, clen, d_slots.data_ptr(), slot_off[:-1], args.level, stream)
-        dg1 = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream)
+        dg1 = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream) if do_md5 else None
         poff = ctx.pack_streams_device(d_slots.data_ptr(), slot_off[:-1], res, d_packed.data_ptr(), stream)
         # records: one per stream (split chunks give two)
         r_off, r_len, r_raw_off = records_of(res, poff, raw_off)
         rl, st = ctx.inflate_batch_device(d_packed.data_ptr(), r_off, r_len, d_back.data_ptr(), r_raw_off, 0, stream)
-        dg2 = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream)
+        dg2 = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream) if do_md5 else None
         state.update(res=res, dg1=dg1, dg2=dg2, rl=rl, st=st, poff=poff, r_raw_off=r_raw_off)
 
     def records_of(res, poff, raw_off):
@@ -315,7 +321,7 @@ def main():
         """inputs in pinned host memory; every copy inside the timed region"""
         d_raw[:U].copy_(h_raw, non_blocking=True)
         res = ctx.deflate_batch_device(d_raw.data_ptr(), coff, clen, d_slots.data_ptr(), slot_off[:-1], args.level, stream)
-        dg1 = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream)
+        dg1 = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream) if do_md5 else None
         poff = ctx.pack_streams_device(d_slots.data_ptr(), slot_off[:-1], res, d_packed.data_ptr(), stream)
         C = int(poff[-1])
         h_comp[:C].copy_(d_packed[:C], non_blocking=True)       # compressed payloads -> host (what gets written to .zwz)
@@ -323,7 +329,7 @@ def main():
         d_packed[:C].copy_(h_comp[:C], non_blocking=True)       # decompress side starts from host bytes again
         r_off, r_len, r_raw_off = records_of(res, poff, raw_off)
         rl, st = ctx.inflate_batch_device(d_packed.data_ptr(), r_off, r_len, d_back.data_ptr(), r_raw_off, 0, stream)
-        dg2 = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream)
+        dg2 = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream) if do_md5 else None
         h_back.copy_(d_back[:U], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         state.update(C=C, dg1=dg1, dg2=dg2)
@@ -341,7 +347,7 @@ def main():
     res = state["res"]
     Cbytes = int(res["len0"].sum() + res["len1"].sum())
     assert (state["st"] == 0).all(), "inflate status"
-    assert np.array_equal(state["dg1"], state["dg2"]), "MD5 verify failed"
+    assert (not do_md5) or np.array_equal(state["dg1"], state["dg2"]), "MD5 verify failed"
     back = d_back[:U].cpu().numpy()
     assert np.array_equal(back, buf), "round trip mismatch"
 
@@ -399,7 +405,7 @@ def main():
         ms = {k: v[0] for k, v in prof.items()}
         nl = {k: v[1] for k, v in prof.items()}
         # dominant kernel by device time on rank 0
-        dom = max(("lz_match", "deflate_encode", "inflate", "md5"), key=lambda k: ms[k])
+        dom = max(("lz_match", "deflate_encode", "inflate") + (("md5",) if do_md5 else ()), key=lambda k: ms[k])
         alg_bytes = {"lz_match": U, "deflate_encode": U + Cbytes, "inflate": U + Cbytes, "md5": 2 * U}[dom] * K  # per K steps on rank 0
         achieved = alg_bytes / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
         traffic = None
@@ -410,13 +416,13 @@ def main():
         line = {
             "metric": METRIC, "value": U_all * K / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": desc, "step": "deflate+MD5(src)+pack+inflate+MD5(out), all through the C ABI", "chunks": int(n_all),
+            "config": {"workload": desc, "step": ("deflate+MD5(src)+pack+inflate+MD5(out)" if do_md5 else "deflate+pack+inflate (no MD5: one file = one serial chain)") + ", all through the C ABI", "chunks": int(n_all),
                        "files": int(nf_all), "uncompressed_bytes": int(U_all), "l2": "inputs (>= 2 GB/GPU) exceed the 126 MB L2",
                        "level": args.level, "parallelism": f"files dealt size-descending round-robin over {world} GPU(s)"},
             "ratio": U_all / C_all,
             "deflate_gbs": U * K / ((ms["lz_match"] + ms["deflate_encode"]) * 1e-3) / 1e9,
             "inflate_gbs": U * K / (ms["inflate"] * 1e-3) / 1e9,
-            "md5_gbs": 2 * U * K / (ms["md5"] * 1e-3) / 1e9,
+            "md5_gbs": (2 * U * K / (ms["md5"] * 1e-3) / 1e9) if do_md5 and ms["md5"] > 0 else None,
             "kernel_ms_per_step": {k: v / K for k, v in ms.items()},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -430,7 +436,7 @@ def main():
             target = int(args.cpu_sample_mb * 1e6) if args.cpu_sample_mb else int(min(8e6 * cores, 400e6))
             sb, so, what = sample_of(buf, foffs, target)
             scoff, sclen, _, _ = corpus.chunk_table(so)
-            dt, comp, ok = cpu_step(sb, so, scoff, sclen, cores)
+            dt, comp, ok = cpu_step(sb, so, scoff, sclen, cores, do_md5)
             # our size on the very same sample, for the ratio criterion
             sres = ctx.deflate_batch(sb, scoff, sclen, args.level)[2]
             ours = int(sres["len0"].sum() + sres["len1"].sum())

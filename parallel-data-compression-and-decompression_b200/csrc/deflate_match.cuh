@@ -148,26 +148,37 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         // ---- 3. warp 0: exact chain build ----
+        // The only true dependency between consecutive steps is head[]: step i+1 may read it only after step i wrote it.
+        // Everything else (hash fetch, __match_any_sync, group roles) is computed one step ahead so the serial chain per
+        // step is one LDS (head) + two STS.
         if (wid == 0) {
+            uint32_t p = lane;
+            uint32_t h = p < nhash ? (uint32_t) prev[p] : 0x10000u + lane; // out-of-range lanes form singleton groups
+            unsigned grp = __match_any_sync(ZWZ_FULL, h);
             for (uint32_t p0 = 0; p0 < nhash; p0 += 32u) {
-                uint32_t p = p0 + lane;
-                bool valid = p < nhash;
-                uint32_t h = valid ? (uint32_t) prev[p] : 0x10000u + lane; // out-of-range lanes form singleton groups
-                unsigned grp = __match_any_sync(ZWZ_FULL, h);
+                // prefetch the next step's hash and grouping before this step's stores
+                const uint32_t pn = p0 + 32u + lane;
+                const uint32_t hn = pn < nhash ? (uint32_t) prev[pn] : 0x10000u + lane;
+                const unsigned grpn = __match_any_sync(ZWZ_FULL, hn);
+                const bool valid = p < nhash;
+                const unsigned lower = grp & ((1u << lane) - 1u);
+                uint32_t pv = p0 + (31u - (uint32_t) __clz((int) lower));
+                if (valid && lower == 0u) pv = head[h];
+                __syncwarp(); // every head[] read of this step precedes its writes
                 if (valid) {
-                    unsigned lower = grp & ((1u << lane) - 1u);
-                    uint32_t pv = lower ? p0 + (31u - (uint32_t) __clz((int) lower)) : (uint32_t) head[h];
                     prev[p] = (uint16_t) pv;
+                    if ((grp >> lane) == 1u) head[h] = (uint16_t) p;
                 }
-                __syncwarp();
-                if (valid && (grp >> lane) == 1u) head[h] = (uint16_t) p;
-                if ((p0 & 96u) == 96u) { // publish every 4 steps
+                if ((p0 & 224u) == 224u) { // publish the front every 8 steps
                     __threadfence_block();
                     __syncwarp();
                     if (lane == 0) ctl->front = p0 + 32u;
                 } else {
                     __syncwarp();
                 }
+                p = pn;
+                h = hn;
+                grp = grpn;
             }
             __threadfence_block();
             __syncwarp();
