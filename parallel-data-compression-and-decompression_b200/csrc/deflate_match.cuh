@@ -192,7 +192,10 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             tile = __shfl_sync(ZWZ_FULL, tile, 0);
             if (tile >= ntiles) break;
             const uint32_t need = (tile + 1u) * 32u < nhash ? (tile + 1u) * 32u : nhash;
-            while (ctl->front < need) ZWZ_SPIN_PAUSE();
+            // Searchers that caught up with the build front must get out of its way: a polling warp burns issue slots of the
+            // scheduler it may share with the builder (measured: 8 polling warps slowed the builder 6x), so back off
+            // exponentially — the front moves 256 positions every ~0.5 us.
+            for (uint32_t ns = 200u; ctl->front < need; ns = ns < 3200u ? ns * 2u : ns) ZWZ_SPIN_SLEEP(ns);
             __threadfence_block();
 
             const uint32_t p = tile * 32u + lane;

@@ -13,12 +13,14 @@
 #define ZWZ_KERNEL static void
 #define ZWZ_DYN_SMEM(name) unsigned char *name = simt::dyn_smem()
 #define ZWZ_SPIN_PAUSE() zwz_emu_spin_pause()
+#define ZWZ_SPIN_SLEEP(ns) zwz_emu_spin_pause()
 #else
 #include <cuda_runtime.h>
 #define ZWZ_DEV __device__ __forceinline__
 #define ZWZ_KERNEL __global__ void
 #define ZWZ_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define ZWZ_SPIN_PAUSE() __nanosleep(20)
+#define ZWZ_SPIN_SLEEP(ns) __nanosleep(ns)
 #endif
 
 #define ZWZ_FULL 0xffffffffu
