@@ -6,9 +6,10 @@
 //   1. the chunk is staged HBM -> shared memory with one bulk asynchronous copy (cp.async.bulk + mbarrier, SASS UBLKCP),
 //      a 16-byte aligned superset of the chunk; the chunk itself starts at byte `skew` of the staging buffer;
 //   2. all threads hash every position (3-byte multiplicative hash) into prev[] in parallel;
-//   3. warp 0 turns the hashes into EXACT hash chains, 32 positions per step: lanes with the same hash inside the step
-//      are linked with __match_any_sync, the lowest lane of a group links to the head table, the highest becomes the new
-//      head. Chains are final behind the build front, which is published through a shared-memory counter;
+//   3. warp 0 turns the hashes into EXACT hash chains, 32 positions per step: every lane links to the old head and
+//      becomes the new head; lanes sharing a hash inside the step are found by reading the head back and repaired with
+//      ballot + shuffle (lowest lane keeps the old head, the others link to the nearest earlier lane, the highest stays
+//      head). Chains are final behind the build front, which is published through a shared-memory counter;
 //   4. the other warps (and warp 0 once it is done) pull 32-position tiles and, one lane per position, walk the chain:
 //      byte checks around the current best length reject most candidates, survivors are compared 4 bytes at a time on
 //      funnel-shifted aligned words; `depth` candidates at most, stop at `nice` bytes;
@@ -148,26 +149,40 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         // ---- 3. warp 0: exact chain build ----
-        // The only true dependency between consecutive steps is head[]: step i+1 may read it only after step i wrote it.
-        // Everything else (hash fetch, __match_any_sync, group roles) is computed one step ahead so the serial chain per
-        // step is one LDS (head) + two STS.
+        // 32 positions per step. Common case (all 32 hashes distinct): read the old head, store it as the link, store the
+        // position as the new head. Lanes that share a hash inside the step are detected by reading the head back (one of
+        // them won the store race, the others see a foreign position) and repaired group by group with ballot + shuffle,
+        // which costs per COLLIDING group — __match_any_sync would cost per DISTINCT value (measured ~600 cycles per step
+        // on sm_100a, which made this warp the bottleneck of the whole kernel).
         if (wid == 0) {
-            uint32_t p = lane;
-            uint32_t h = p < nhash ? (uint32_t) prev[p] : 0x10000u + lane; // out-of-range lanes form singleton groups
-            unsigned grp = __match_any_sync(ZWZ_FULL, h);
+            const unsigned lt = (1u << lane) - 1u;
+            uint32_t hn = lane < nhash ? (uint32_t) prev[lane] : 0u;
             for (uint32_t p0 = 0; p0 < nhash; p0 += 32u) {
-                // prefetch the next step's hash and grouping before this step's stores
-                const uint32_t pn = p0 + 32u + lane;
-                const uint32_t hn = pn < nhash ? (uint32_t) prev[pn] : 0x10000u + lane;
-                const unsigned grpn = __match_any_sync(ZWZ_FULL, hn);
+                const uint32_t p = p0 + lane;
                 const bool valid = p < nhash;
-                const unsigned lower = grp & ((1u << lane) - 1u);
-                uint32_t pv = p0 + (31u - (uint32_t) __clz((int) lower));
-                if (valid && lower == 0u) pv = head[h];
-                __syncwarp(); // every head[] read of this step precedes its writes
+                const uint32_t h = hn;
+                const uint32_t pn = p + 32u;
+                hn = pn < nhash ? (uint32_t) prev[pn] : 0u; // next step's hash, fetched ahead of this step's stores
+                uint32_t old = ZWZ_DM_NIL;
+                if (valid) old = head[h];
+                __syncwarp(); // all reads of head[] precede the writes of this step
                 if (valid) {
-                    prev[p] = (uint16_t) pv;
-                    if ((grp >> lane) == 1u) head[h] = (uint16_t) p;
+                    prev[p] = (uint16_t) old;
+                    head[h] = (uint16_t) p;
+                }
+                __syncwarp();
+                uint32_t rb = valid ? (uint32_t) head[h] : p;
+                unsigned rem = __ballot_sync(ZWZ_FULL, rb != p); // lanes that lost a store race
+                while (rem) {                                    // one round per colliding group (warp-uniform loop)
+                    const int leader = __ffs((int) rem) - 1;
+                    const uint32_t hl = __shfl_sync(ZWZ_FULL, h, leader);
+                    const unsigned same = __ballot_sync(ZWZ_FULL, valid && h == hl);
+                    if (valid && h == hl) {
+                        const unsigned lower = same & lt;
+                        if (lower) prev[p] = (uint16_t) (p0 + 31u - (uint32_t) __clz((int) lower)); // nearest earlier lane
+                        if ((same >> lane) == 1u) head[h] = (uint16_t) p;                               // highest lane is the new head
+                    }
+                    rem &= ~same;
                 }
                 if ((p0 & 224u) == 224u) { // publish the front every 8 steps
                     __threadfence_block();
@@ -176,9 +191,6 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 } else {
                     __syncwarp();
                 }
-                p = pn;
-                h = hn;
-                grp = grpn;
             }
             __threadfence_block();
             __syncwarp();
