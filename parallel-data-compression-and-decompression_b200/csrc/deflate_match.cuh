@@ -5,12 +5,16 @@
 // Per chunk (persistent CTAs, chunks handed out by an atomic counter):
 //   1. the chunk is staged HBM -> shared memory with one bulk asynchronous copy (cp.async.bulk + mbarrier, SASS UBLKCP),
 //      a 16-byte aligned superset of the chunk; the chunk itself starts at byte `skew` of the staging buffer;
-//   2. all threads hash every position (3-byte multiplicative hash) into prev[] in parallel;
-//   3. warp 0 turns the hashes into EXACT hash chains, 32 positions per step: every lane links to the old head and
+//   2. all threads hash every position (3-byte multiplicative hash) into prev[] in parallel, and the positions are
+//      split — stably, so each list stays sorted by position — into one list per warp by the top bits of the hash
+//      (ballot-based multi-split: per-warp counts, one small scan, scatter to the chunk's scratch in HBM/L2);
+//   3. every warp turns ITS list into EXACT hash chains, 32 positions per step: every lane links to the old head and
 //      becomes the new head; lanes sharing a hash inside the step are found by reading the head back and repaired with
 //      ballot + shuffle (lowest lane keeps the old head, the others link to the nearest earlier lane, the highest stays
-//      head). Chains are final behind the build front, which is published through a shared-memory counter;
-//   4. the other warps (and warp 0 once it is done) pull 32-position tiles and, one lane per position, walk the chain:
+//      head). Lists cover disjoint hash ranges, so the builders share head[] without ever touching the same entry — the
+//      serial insertion order a hash chain needs is kept per hash value, and the chunk-long serial loop of a
+//      single-builder design (measured: it was the kernel's critical path) becomes NW loops 1/NW as long;
+//   4. all warps pull 32-position tiles and, one lane per position, walk the chain:
 //      byte checks around the current best length reject most candidates, survivors are compared 4 bytes at a time on
 //      funnel-shifted aligned words; `depth` candidates at most, stop at `nice` bytes;
 //   5. the best (length, distance) of EVERY position goes to the chunk's scratch in HBM (4 bytes per input byte,
@@ -35,26 +39,31 @@ namespace zwz {
 
 template <int CLS> struct MatchClass;
 template <> struct MatchClass<0> {
-    static constexpr uint32_t kCap = 8192, kThreads = 256, kHBits = 12, kData = 8192 + 64;
-    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+    static constexpr uint32_t kCap = 8192, kThreads = 256, kHBits = 12, kData = 8192 + 64, kListBits = 3;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 8u * 8u;
 };
 template <> struct MatchClass<1> {
-    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64;
-    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64, kListBits = 4;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<2> {
-    static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600;
-    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 512u;
+    static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600, kListBits = 5;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 640u + 2u * 32u * 32u;
 };
 
+// control block (after the tables); cnt[NW][NW] u16 follows it
 struct MatchCtl {
     unsigned long long mbar;   // mbarrier for the bulk copy
-    volatile uint32_t front;   // positions < front have final chains
     uint32_t next_tile;
     uint32_t cur_work;
-    uint32_t pad;
+    uint32_t base[33];         // list k = entries [base[k], base[k+1]) of the position list
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
+static_assert(sizeof(MatchCtl) <= 640, "MatchCtl must fit its slot");
+
+// scratch layout of one chunk (uint32 units): [0, A) best match per position, then tokens in place (deflate_encode.cuh);
+// [A, A + B) the hash-partitioned position lists (u16) used only inside lz_match_kernel
+ZWZ_DEV uint32_t dm_scratch_match_words(uint32_t n) { return (n + 2u + 31u) & ~31u; }
 
 template <int HBITS> ZWZ_DEV uint32_t dm_hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
     uint32_t v = b0 | (b1 << 8) | (b2 << 16);
@@ -90,14 +99,17 @@ template <int CLS>
 ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJob job, const uint32_t *__restrict__ order, uint32_t n_work,
                                                                          uint32_t *work_counter) {
     constexpr uint32_t T = MatchClass<CLS>::kThreads, HB = MatchClass<CLS>::kHBits, DATA = MatchClass<CLS>::kData;
-    constexpr uint32_t NW = T / 32u;
+    constexpr uint32_t NW = T / 32u, LB = MatchClass<CLS>::kListBits;
+    static_assert((1u << LB) == NW, "one position list per warp");
     ZWZ_DYN_SMEM(smem);
     const uint32_t *dataw = (const uint32_t *) smem;                                  // chunk bytes as aligned words
     uint16_t *prev = (uint16_t *) (smem + DATA);
     uint16_t *head = (uint16_t *) (smem + DATA + MatchClass<CLS>::kPrevBytes);
     MatchCtl *ctl = (MatchCtl *) (smem + DATA + MatchClass<CLS>::kPrevBytes + (2u << HB));
+    uint16_t *cnt = (uint16_t *) ((unsigned char *) ctl + 640);                       // [NW][NW]: running list offsets per (warp, list)
     const uint8_t *datab = (const uint8_t *) smem;
     const unsigned tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const unsigned lt = (1u << lane) - 1u;
     uint32_t parity = 0;
 
 #ifndef ZWZ_EMU
@@ -123,10 +135,8 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         for (uint32_t i = tid; i < skew + n; i += T) smem[i] = i < skew ? 0 : src[i - skew];
 #endif
         for (uint32_t i = tid; i < (1u << HB) / 2u; i += T) ((uint32_t *) head)[i] = 0xffffffffu;
-        if (tid == 0) {
-            ctl->front = 0;
-            ctl->next_tile = 0;
-        }
+        for (uint32_t i = tid; i < NW * NW / 2u; i += T) ((uint32_t *) cnt)[i] = 0u;
+        if (tid == 0) ctl->next_tile = 0;
 #ifndef ZWZ_EMU
         if (stage_bytes) dm_mbar_wait(&ctl->mbar, parity);
         parity ^= (stage_bytes != 0u);
@@ -138,77 +148,123 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         uint32_t *mout = job.scratch + job.scr_off[c];
+        uint16_t *list = (uint16_t *) (mout + dm_scratch_match_words(n));
         const uint32_t nhash = n >= 3u ? n - 2u : 0u; // positions that own a 3-byte hash
         const uint32_t ntiles = (n + 31u) >> 5;
+        const uint32_t nsteps = (nhash + 31u) >> 5;
+        const uint32_t spw = (nsteps + NW - 1u) / NW;  // steps per warp: warp w owns positions [w*spw*32, (w+1)*spw*32)
 
-        // ---- 2. hash every position (parallel); prev[p] holds hash(p) until the builder replaces it by the link ----
-        for (uint32_t p = tid; p < nhash; p += T) {
-            uint32_t v = ld32u(dataw, skew + p);
-            prev[p] = (uint16_t) dm_hash3<HB>(v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu);
+        // ---- 2. hash every position; count, per warp, how many of its positions fall in each of the NW hash ranges ----
+        // Same-range lanes of a step are found with LB ballots (a 5-bit match_any), so ranks inside a step follow lane
+        // (= position) order and the lists come out sorted by position.
+        for (uint32_t st = wid * spw; st < (wid + 1u) * spw && st < nsteps; ++st) {
+            const uint32_t p = st * 32u + lane;
+            const bool valid = p < nhash;
+            uint32_t h = 0;
+            if (valid) {
+                uint32_t v = ld32u(dataw, skew + p);
+                h = dm_hash3<HB>(v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu);
+                prev[p] = (uint16_t) h; // prev[p] holds hash(p) until the builder replaces it by the link
+            }
+            const uint32_t b = h >> (HB - LB);
+            unsigned m = __ballot_sync(ZWZ_FULL, valid);
+#pragma unroll
+            for (uint32_t k = 0; k < LB; ++k) {
+                unsigned v = __ballot_sync(ZWZ_FULL, (b >> k) & 1u);
+                m &= ((b >> k) & 1u) ? v : ~v;
+            }
+            if (valid && (m >> lane) == 1u) cnt[wid * NW + b] += (uint16_t) __popc(m); // entry owned by this warp
+            __syncwarp();
         }
         __syncthreads();
-
-        // ---- 3. warp 0: exact chain build ----
-        // 32 positions per step. Common case (all 32 hashes distinct): read the old head, store it as the link, store the
-        // position as the new head. Lanes that share a hash inside the step are detected by reading the head back (one of
-        // them won the store race, the others see a foreign position) and repaired group by group with ballot + shuffle,
-        // which costs per COLLIDING group — __match_any_sync would cost per DISTINCT value (measured ~600 cycles per step
-        // on sm_100a, which made this warp the bottleneck of the whole kernel).
+        // ---- 3. offsets: list b = [base[b], base[b+1]), inside it warp 0's positions first, then warp 1's, ... ----
         if (wid == 0) {
-            const unsigned lt = (1u << lane) - 1u;
-            uint32_t hn = lane < nhash ? (uint32_t) prev[lane] : 0u;
-            for (uint32_t p0 = 0; p0 < nhash; p0 += 32u) {
-                const uint32_t p = p0 + lane;
-                const bool valid = p < nhash;
-                const uint32_t h = hn;
-                const uint32_t pn = p + 32u;
-                hn = pn < nhash ? (uint32_t) prev[pn] : 0u; // next step's hash, fetched ahead of this step's stores
+            uint32_t run = 0;
+            if (lane < NW) {
+                for (uint32_t ww = 0; ww < NW; ++ww) {
+                    uint32_t t = cnt[ww * NW + lane];
+                    cnt[ww * NW + lane] = (uint16_t) run;
+                    run += t;
+                }
+            }
+            uint32_t incl = warp_incl_scan(run);
+            if (lane < NW) ctl->base[lane] = incl - run;
+            if (lane == NW - 1u) ctl->base[NW] = incl;
+        }
+        __syncthreads();
+        // ---- 4. scatter positions into the lists (stable) ----
+        for (uint32_t st = wid * spw; st < (wid + 1u) * spw && st < nsteps; ++st) {
+            const uint32_t p = st * 32u + lane;
+            const bool valid = p < nhash;
+            const uint32_t h = valid ? (uint32_t) prev[p] : 0u;
+            const uint32_t b = h >> (HB - LB);
+            unsigned m = __ballot_sync(ZWZ_FULL, valid);
+#pragma unroll
+            for (uint32_t k = 0; k < LB; ++k) {
+                unsigned v = __ballot_sync(ZWZ_FULL, (b >> k) & 1u);
+                m &= ((b >> k) & 1u) ? v : ~v;
+            }
+            if (valid) {
+                uint32_t slot = ctl->base[b] + cnt[wid * NW + b] + (uint32_t) __popc(m & lt);
+                list[slot] = (uint16_t) p;
+            }
+            __syncwarp();
+            if (valid && (m >> lane) == 1u) cnt[wid * NW + b] += (uint16_t) __popc(m);
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncthreads();
+
+        // ---- 5. EXACT hash chains, one warp per list, 32 positions per step ----
+        // Lists hold disjoint hash ranges, so the NW builders never touch the same head[] entry. Common case (all 32 hashes
+        // of a step distinct): read the old head, store it as the link, store the position as the new head. Lanes that
+        // share a hash inside the step are detected by reading the head back (one of them won the store race, the others see
+        // a foreign position) and repaired group by group with ballot + shuffle, which costs per COLLIDING group —
+        // __match_any_sync costs per DISTINCT value (measured ~600 cycles per step on sm_100a).
+        {
+            const uint32_t i_end = ctl->base[wid + 1u];
+            uint32_t i0 = ctl->base[wid];
+            uint32_t qn = (i0 + lane < i_end) ? (uint32_t) __ldcg(list + i0 + lane) : 0u;
+            for (; i0 < i_end; i0 += 32u) {
+                const bool valid = i0 + lane < i_end;
+                const uint32_t q = qn;
+                qn = (i0 + 32u + lane < i_end) ? (uint32_t) __ldcg(list + i0 + 32u + lane) : 0u; // next step, fetched ahead
+                const uint32_t h = valid ? (uint32_t) prev[q] : 0u;
                 uint32_t old = ZWZ_DM_NIL;
                 if (valid) old = head[h];
                 __syncwarp(); // all reads of head[] precede the writes of this step
                 if (valid) {
-                    prev[p] = (uint16_t) old;
-                    head[h] = (uint16_t) p;
+                    prev[q] = (uint16_t) old;
+                    head[h] = (uint16_t) q;
                 }
                 __syncwarp();
-                uint32_t rb = valid ? (uint32_t) head[h] : p;
-                unsigned rem = __ballot_sync(ZWZ_FULL, rb != p); // lanes that lost a store race
+                uint32_t rb = valid ? (uint32_t) head[h] : q;
+                unsigned rem = __ballot_sync(ZWZ_FULL, rb != q); // lanes that lost a store race
                 while (rem) {                                    // one round per colliding group (warp-uniform loop)
                     const int leader = __ffs((int) rem) - 1;
                     const uint32_t hl = __shfl_sync(ZWZ_FULL, h, leader);
-                    const unsigned same = __ballot_sync(ZWZ_FULL, valid && h == hl);
-                    if (valid && h == hl) {
-                        const unsigned lower = same & lt;
-                        if (lower) prev[p] = (uint16_t) (p0 + 31u - (uint32_t) __clz((int) lower)); // nearest earlier lane
-                        if ((same >> lane) == 1u) head[h] = (uint16_t) p;                               // highest lane is the new head
+                    const bool mine = valid && h == hl;
+                    const unsigned same = __ballot_sync(ZWZ_FULL, mine);
+                    const unsigned lower = same & lt;
+                    const int from = (mine && lower) ? 31 - __clz((int) lower) : (int) lane;
+                    const uint32_t qlow = __shfl_sync(ZWZ_FULL, q, from);  // nearest earlier position of the group
+                    if (mine) {
+                        if (lower) prev[q] = (uint16_t) qlow;
+                        if ((same >> lane) == 1u) head[h] = (uint16_t) q;    // the latest position stays head
                     }
                     rem &= ~same;
                 }
-                if ((p0 & 224u) == 224u) { // publish the front every 8 steps
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) ctl->front = p0 + 32u;
-                } else {
-                    __syncwarp();
-                }
+                __syncwarp();
             }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) ctl->front = 0x7fffffffu;
         }
+        __syncthreads();
 
-        // ---- 4. search: one lane per position, 32-position tiles ----
+        // ---- 6. search: one lane per position, 32-position tiles ----
         for (;;) {
             uint32_t tile = 0;
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
             tile = __shfl_sync(ZWZ_FULL, tile, 0);
             if (tile >= ntiles) break;
-            const uint32_t need = (tile + 1u) * 32u < nhash ? (tile + 1u) * 32u : nhash;
-            // Searchers that caught up with the build front must get out of its way: a polling warp burns issue slots of the
-            // scheduler it may share with the builder (measured: 8 polling warps slowed the builder 6x), so back off
-            // exponentially — the front moves 256 positions every ~0.5 us.
-            for (uint32_t ns = 200u; ctl->front < need; ns = ns < 3200u ? ns * 2u : ns) ZWZ_SPIN_SLEEP(ns);
-            __threadfence_block();
 
             const uint32_t p = tile * 32u + lane;
             uint32_t best_len = 2u, best_dist = 0u;
@@ -253,7 +309,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         }
         __syncthreads();
 
-        // ---- 6. Adler-32 of the chunk ----
+        // ---- 7. Adler-32 of the chunk ----
         {
             uint32_t seg = (n + T - 1u) / T;
             uint32_t lo = tid * seg, hi = lo + seg;

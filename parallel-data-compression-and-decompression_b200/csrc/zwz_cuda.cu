@@ -352,7 +352,9 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
             h_scr_off[i] = scr;
             h_out_off[i] = out_off[i];
             h_len[i] = len[i];
-            scr += align_up((size_t) len[i] + 2, 32); // uint32 entries; +1 so the parser may peek one past the end
+            // uint32 entries: best match per position (+ pad so the parser may peek one past the end), then the u16 position
+            // lists of lz_match_kernel (deflate_match.cuh: dm_scratch_match_words)
+            scr += align_up((size_t) len[i] + 2, 32) + align_up(((size_t) len[i] + 1) / 2 + 32, 32);
             raw += len[i];
         }
         max_scr = std::max(max_scr, scr);
