@@ -260,6 +260,8 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         // ---- 6. search: one lane per position, 32-position tiles ----
+        const uint32_t sD = smem_addr(smem) + skew; // shared address of chunk byte 0
+        const uint32_t sP = smem_addr(prev);        // shared address of prev[0]
         for (;;) {
             uint32_t tile = 0;
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
@@ -271,34 +273,35 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             if (p < nhash) {
                 const uint32_t maxlen = (n - p) < ZWZ_MAX_MATCH ? (n - p) : ZWZ_MAX_MATCH;
                 const uint32_t limit = p > ZWZ_MAX_DIST ? p - ZWZ_MAX_DIST : 0u;
-                const uint32_t ap = skew + p;
-                const uint32_t first3 = ld32u(dataw, ap) & 0x00ffffffu;
-                uint32_t scan_end = datab[ap + 2u], scan_end1 = datab[ap + 1u]; // bytes at best_len and best_len - 1
-                uint32_t cand = prev[p];
-                uint32_t budget = job.depth;
-                while (cand != ZWZ_DM_NIL && cand >= limit && budget-- != 0u) {
-                    const uint32_t ac = skew + cand;
-                    const uint32_t nxt = prev[cand]; // next link is fetched while this candidate is examined
+                const uint32_t span = p - limit;            // a candidate is usable iff 0 <= cand - limit < span (NIL fails)
+                const uint32_t ap = sD + p;                 // shared address of the scan position
+                const uint32_t first3 = lds32u(ap) & 0x00ffffffu;
+                uint32_t scan_end = lds8(ap + 2u), scan_end1 = lds8(ap + 1u); // bytes at best_len and best_len - 1
+                uint32_t cand = lds16(sP + 2u * p);
+                for (uint32_t budget = job.depth; budget != 0u && (cand - limit) < span; --budget) {
+                    const uint32_t ac = sD + cand;
+                    const uint32_t nxt = lds16(sP + 2u * cand); // next link is fetched while this candidate is examined
                     // cheap rejects first (zlib's longest_match order): the byte that would extend the best match, its
                     // predecessor, then the 3-byte prefix (hash collisions)
-                    if (datab[ac + best_len] == scan_end && datab[ac + best_len - 1u] == scan_end1 &&
-                        (ld32u(dataw, ac) & 0x00ffffffu) == first3) {
-                        uint32_t len = 3u;
-                        while (len < maxlen) {
-                            uint32_t y = ld32u(dataw, ac + len) ^ ld32u(dataw, ap + len);
-                            if (y) {
-                                len += ((uint32_t) __ffs((int) y) - 1u) >> 3;
-                                break;
+                    if (lds8(ac + best_len) == scan_end) {
+                        if (lds8(ac + best_len - 1u) == scan_end1 && (lds32u(ac) & 0x00ffffffu) == first3) {
+                            uint32_t len = 3u;
+                            while (len < maxlen) {
+                                uint32_t y = lds32u(ac + len) ^ lds32u(ap + len);
+                                if (y) {
+                                    len += ((uint32_t) __ffs((int) y) - 1u) >> 3;
+                                    break;
+                                }
+                                len += 4u;
                             }
-                            len += 4u;
-                        }
-                        if (len > maxlen) len = maxlen;
-                        if (len > best_len) {
-                            best_len = len;
-                            best_dist = p - cand;
-                            if (len >= job.nice || len >= maxlen) break;
-                            scan_end = datab[ap + len];
-                            scan_end1 = datab[ap + len - 1u];
+                            if (len > maxlen) len = maxlen;
+                            if (len > best_len) {
+                                best_len = len;
+                                best_dist = p - cand;
+                                if (len >= job.nice || len >= maxlen) break;
+                                scan_end = lds8(ap + len);
+                                scan_end1 = lds8(ap + len - 1u);
+                            }
                         }
                     }
                     cand = nxt;

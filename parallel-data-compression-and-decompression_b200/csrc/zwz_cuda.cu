@@ -167,8 +167,9 @@ struct LevelParams {
     uint32_t depth, nice;
 };
 LevelParams level_params(int level) {
-    // search effort per level; 0 = default (6)
-    static const LevelParams t[10] = {{32, 128}, {4, 16}, {6, 24}, {8, 32}, {16, 64}, {24, 96}, {32, 128}, {64, 160}, {128, 258}, {512, 258}};
+    // search effort per level (hash-chain candidates per position, stop length). 0 = default: the cheapest setting that
+    // stays inside the 3 % size tolerance on every corpus class (tests/test_kernels.py::test_deflate_ratio...)
+    static const LevelParams t[10] = {{16, 64}, {4, 16}, {6, 24}, {8, 32}, {16, 64}, {24, 96}, {32, 128}, {64, 160}, {128, 258}, {512, 258}};
     if (level < 0 || level > 9) level = 0;
     return t[level];
 }
