@@ -337,6 +337,46 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     extra_bits = warp_sum64(extra_bits);
     __syncwarp();
 
+    // ---------------- near-incompressible chunks are STORED ----------------
+    // Policy: a chunk is stored when the best Huffman encoding would save less than n/256 bytes (0.4 %). zlib would still
+    // emit a dynamic block there (it takes any gain, e.g. 7 002 vs 7 011 bytes on a JPEG-like file), but such a block costs
+    // one Huffman symbol per byte to decode — for our inflate and for the reference's zlib alike — and buys nothing.
+    // First an exact-safe shortcut: no prefix code beats the empirical entropy, so if even the entropy bound cannot save
+    // n/256 bytes the three Huffman constructions below are skipped altogether.
+    const uint32_t sto_bytes = n + 11u;
+    const uint32_t sto_slack = n >> 8;
+    bool force_stored = false;
+    {
+        float nl = 0.f, nd = 0.f, hl_bits = 0.f;
+        for (uint32_t s = lane; s < 320u; s += 32u) {
+            float f = (float) S.freq[s];
+            if (s < ZWZ_DE_DOFF) nl += f; else nd += f;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            nl += __shfl_xor_sync(ZWZ_FULL, nl, d);
+            nd += __shfl_xor_sync(ZWZ_FULL, nd, d);
+        }
+        for (uint32_t s = lane; s < 320u; s += 32u) {
+            float f = (float) S.freq[s];
+            if (f > 0.f) hl_bits += f * (zwz_log2f(s < ZWZ_DE_DOFF ? nl : nd) - zwz_log2f(f));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) hl_bits += __shfl_xor_sync(ZWZ_FULL, hl_bits, d);
+        float bound_bytes = (hl_bits + (float) extra_bits) * 0.125f + 7.f; // + zlib wrapper and block header
+        force_stored = bound_bytes * 0.9995f >= (float) sto_bytes - (float) sto_slack && sto_bytes <= ZWZ_CHUNK;
+    }
+    if (force_stored) {
+        uint32_t l0 = enc_stored_stream(out, src, n, job.adler[c]);
+        if (lane == 0) {
+            job.res[4u * c + 0u] = l0;
+            job.res[4u * c + 1u] = 0u;
+            job.res[4u * c + 2u] = n;
+            job.res[4u * c + 3u] = 0u;
+        }
+        return;
+    }
+
     // ---------------- codes ----------------
     enc_huffman(S, S.freq, ZWZ_DE_LL, 15u, S.blen, S.code);
     enc_huffman(S, S.freq + ZWZ_DE_DOFF, ZWZ_DE_D, 15u, S.blen + ZWZ_DE_DOFF, S.code + ZWZ_DE_DOFF);
@@ -430,13 +470,12 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     const uint64_t fix_total = 3u + fix_bits;
     const uint32_t dyn_bytes = (uint32_t) ((dyn_total + 7u) >> 3) + 6u;
     const uint32_t fix_bytes = (uint32_t) ((fix_total + 7u) >> 3) + 6u;
-    const uint32_t sto_bytes = n + 11u;
     uint32_t btype = 2u, best = dyn_bytes;
     if (fix_bytes <= best) {
         btype = 1u;
         best = fix_bytes;
     }
-    if (sto_bytes < best) {
+    if (sto_bytes <= best + sto_slack) { // see the policy above
         btype = 0u;
         best = sto_bytes;
     }

@@ -547,10 +547,19 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
             uint32_t want = ((uint32_t) comp[bpos] << 24) | ((uint32_t) comp[bpos + 1] << 16) | ((uint32_t) comp[bpos + 2] << 8) | comp[bpos + 3];
             // a = 1 + sum(byte), b = n + sum((n - j) * byte_j)  (mod 65521)
             uint64_t s0 = 0, s1 = 0;
-            for (uint32_t j = lane; j < pos; j += 32u) {
-                uint32_t v = ((volatile uint8_t *) out)[j];
-                s0 += v;
-                s1 += (uint64_t) (j % 65521u) * v;
+            if (pos < 131042u) { // j mod 65521 is one conditional subtract (every record the reference writes is here)
+                for (uint32_t j = lane; j < pos; j += 32u) {
+                    uint32_t v = ((volatile uint8_t *) out)[j];
+                    uint32_t jm = j >= 65521u ? j - 65521u : j;
+                    s0 += v;
+                    s1 += (uint64_t) jm * v;
+                }
+            } else {
+                for (uint32_t j = lane; j < pos; j += 32u) {
+                    uint32_t v = ((volatile uint8_t *) out)[j];
+                    s0 += v;
+                    s1 += (uint64_t) (j % 65521u) * v;
+                }
             }
             s0 = warp_sum64(s0) % 65521u;
             s1 = warp_sum64(s1 % 65521u) % 65521u;

@@ -23,6 +23,12 @@
 #define ZWZ_SPIN_SLEEP(ns) __nanosleep(ns)
 #endif
 
+#ifdef ZWZ_EMU
+#include <cmath>
+#define zwz_log2f(x) log2f(x)
+#else
+#define zwz_log2f(x) __log2f(x)
+#endif
 #define ZWZ_FULL 0xffffffffu
 #define ZWZ_CHUNK 65535u
 #define ZWZ_MIN_MATCH 3u
