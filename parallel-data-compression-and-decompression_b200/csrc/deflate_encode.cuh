@@ -348,10 +348,13 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     bool force_stored = false;
     {
         float nl = 0.f, nd = 0.f, hl_bits = 0.f;
+        uint32_t nused = 0;
         for (uint32_t s = lane; s < 320u; s += 32u) {
             float f = (float) S.freq[s];
             if (s < ZWZ_DE_DOFF) nl += f; else nd += f;
+            nused += f > 0.f ? 1u : 0u;
         }
+        nused = warp_sum(nused);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             nl += __shfl_xor_sync(ZWZ_FULL, nl, d);
@@ -363,8 +366,10 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) hl_bits += __shfl_xor_sync(ZWZ_FULL, hl_bits, d);
-        float bound_bytes = (hl_bits + (float) extra_bits) * 0.125f + 7.f; // + zlib wrapper and block header
-        force_stored = bound_bytes * 0.9995f >= (float) sto_bytes - (float) sto_slack && sto_bytes <= ZWZ_CHUNK;
+        // + zlib wrapper and block header, + ~2 bits per used symbol for a dynamic header (a small random sample sits ~23
+        // bytes under 8 bits/byte of empirical entropy; its code-length header costs several times that)
+        float bound_bytes = (hl_bits + (float) extra_bits) * 0.125f + 7.f + (float) (nused >> 2);
+        force_stored = bound_bytes * 0.9995f >= (float) sto_bytes - (float) sto_slack && sto_bytes <= ZWZ_CHUNK && n >= 512u;
     }
     if (force_stored) {
         uint32_t l0 = enc_stored_stream(out, src, n, job.adler[c]);

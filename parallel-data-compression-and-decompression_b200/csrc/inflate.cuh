@@ -429,26 +429,52 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
 
         // ---- symbol loop ----
         for (;;) {
-            infb_refill(B); // >= 33 bits: room for two literal/length codes before the next refill
-            uint32_t e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
-            uint32_t kind = (e >> 8) & 3u;
-            uint32_t nb = e & 15u;
-            if (kind == INF_KIND_LIT && INF_NEED(nb)) { // hot path: literal, then look at the next code right away
-                infb_drop(B, nb);
-                if (lane == (pos & 31u)) mybyte = e >> 16;
-                pos++;
-                if ((pos & 31u) == 0u) INF_FLUSH_LITS();
-                e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
-                kind = (e >> 8) & 3u;
-                nb = e & 15u;
-                if (kind == INF_KIND_LIT && INF_NEED(nb)) {
-                    infb_drop(B, nb);
-                    if (lane == (pos & 31u)) mybyte = e >> 16;
-                    pos++;
-                    if ((pos & 31u) == 0u) INF_FLUSH_LITS();
+            infb_refill(B); // >= 33 valid bits
+            uint32_t e;
+            if (B.fed <= total_bits) {
+                // Literal runs, 32 bit offsets at a time ("warp-ballot symbol decode"): lane l decodes the code that WOULD
+                // start at bit l of the buffer; the ballot says which offsets hold a complete literal; the offsets that
+                // really are code starts form the chain 0 -> nb(0) -> ..., recovered with 5 rounds of pointer doubling on
+                // (reach mask, jump) pairs. All literals on the chain are stored by their lanes in one go and the whole
+                // run is dropped from the bit buffer at once. The chain ends at the first non-literal (handled below) or
+                // past offset 31.
+                const uint32_t el = S.lit[(uint32_t) (B.hold >> lane) & ((1u << ZWZ_INF_LBITS) - 1u)];
+                const bool ok = (lane + 15u <= B.cnt) && ((el >> 8) & 3u) == INF_KIND_LIT;
+                const unsigned litmask = __ballot_sync(ZWZ_FULL, ok);
+                if (litmask & 1u) {
+                    uint32_t J = lane + (el & 15u);
+                    uint32_t R = ok ? (1u << lane) : 0u;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const bool go = ok && J < 32u && ((litmask >> J) & 1u);
+                        const int from = go ? (int) J : (int) lane;
+                        const uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);
+                        const uint32_t Jj = __shfl_sync(ZWZ_FULL, J, from);
+                        if (go) {
+                            R |= Rj;
+                            J = Jj;
+                        }
+                    }
+                    const uint32_t R0 = __shfl_sync(ZWZ_FULL, R, 0);
+                    const uint32_t J0 = __shfl_sync(ZWZ_FULL, J, 0);
+                    const uint32_t nlit = (uint32_t) __popc(R0);
+                    INF_FLUSH_LITS();
+                    if ((R0 >> lane) & 1u) {
+                        const uint32_t q = pos + (uint32_t) __popc(R0 & ((1u << lane) - 1u));
+                        if (q < cap) out[q] = (uint8_t) (el >> 16);
+                    }
+                    if (pos + nlit > cap) overflow = true;
+                    pos += nlit;
+                    pend_lo = pos;
+                    infb_drop(B, J0);
                     continue;
                 }
+                e = __shfl_sync(ZWZ_FULL, el, 0);
+            } else {
+                e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
             }
+            uint32_t kind = (e >> 8) & 3u;
+            uint32_t nb = e & 15u;
             if (kind == INF_KIND_SPECIAL) {
                 if ((e >> 4) & 15u) { // code longer than the table index: canonical walk (complete sets only get here)
                     uint32_t len = 0;
