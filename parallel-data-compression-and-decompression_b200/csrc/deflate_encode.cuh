@@ -290,12 +290,15 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     // ---------------- parse ----------------
     uint32_t ntok = 0;
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)
+    uint32_t m0 = lane < n ? m[lane] : 0u;
     for (uint32_t p = 0; p < n;) {
         uint32_t q = p + lane;
-        uint32_t m0 = q < n ? m[q] : 0u;
+        // the window after this one, fetched before it is known to be needed: when the window holds no match that leaves
+        // it (J0 == 32: every literal-only stretch) the next step starts without waiting on a dependent load
+        const uint32_t mnx = q + 32u < n ? m[q + 32u] : 0u;
         uint32_t m1 = __shfl_down_sync(ZWZ_FULL, m0, 1);
-        uint32_t mnext = (lane == 31u && q + 1u < n) ? m[q + 1u] : 0u;
-        if (lane == 31u) m1 = mnext;
+        const uint32_t mfirst = __shfl_sync(ZWZ_FULL, mnx, 0);
+        if (lane == 31u) m1 = mfirst;
         uint32_t len0 = m0 >> 16, len1 = m1 >> 16;
         bool take = len0 >= ZWZ_MIN_MATCH && !(len1 > len0);
         uint32_t J = lane + (take ? len0 : 1u);
@@ -332,6 +335,8 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         }
         ntok += (uint32_t) __popc(tm);
         p += J0;
+        if (J0 == 32u) m0 = mnx;
+        else m0 = p + lane < n ? m[p + lane] : 0u;
     }
     if (lane == 0) S.freq[256] += 1u; // end of block
     extra_bits = warp_sum64(extra_bits);
@@ -588,11 +593,17 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     }
 }
 
-ZWZ_KERNEL __launch_bounds__(ZWZ_DE_WARPS * 32) deflate_encode_kernel(DeflateJob job) {
+// Persistent warps pulling chunks from a global counter (same reason as inflate_kernel: no idle warps behind a long chunk).
+ZWZ_KERNEL __launch_bounds__(ZWZ_DE_WARPS * 32) deflate_encode_kernel(DeflateJob job, uint32_t *work_counter) {
     __shared__ EncWarpSmem smem[ZWZ_DE_WARPS];
-    uint32_t c = blockIdx.x * ZWZ_DE_WARPS + warp_id();
-    if (c >= job.n) return;
-    enc_chunk(smem[warp_id()], job, c);
+    for (;;) {
+        uint32_t c = 0;
+        if (lane_id() == 0) c = atomicAdd(work_counter, 1u);
+        c = __shfl_sync(ZWZ_FULL, c, 0);
+        if (c >= job.n) break;
+        enc_chunk(smem[warp_id()], job, c);
+        __syncwarp();
+    }
 }
 
 } // namespace zwz

@@ -605,19 +605,27 @@ done:
 #undef INF_NEED
 }
 
-ZWZ_KERNEL inflate_kernel(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
-                          uint8_t *raw_out, const uint64_t *__restrict__ raw_off, uint32_t *raw_len, uint32_t *status, uint32_t n,
-                          uint32_t flags) {
+// Persistent warps: every warp pulls the next stream from a global counter, so a CTA is never kept alive by one long stream
+// while its other warps idle (streams of one batch differ in length by 100x in config C2).
+ZWZ_KERNEL __launch_bounds__(ZWZ_INF_WARPS * 32) inflate_kernel(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ off,
+                                                              const uint32_t *__restrict__ len, uint8_t *raw_out,
+                                                              const uint64_t *__restrict__ raw_off, uint32_t *raw_len, uint32_t *status,
+                                                              uint32_t n, uint32_t flags, uint32_t *work_counter) {
     __shared__ InflateWarpSmem smem[ZWZ_INF_WARPS];
-    uint32_t sid = blockIdx.x * ZWZ_INF_WARPS + warp_id();
-    if (sid >= n) return;
-    uint64_t cap64 = raw_off[sid + 1] - raw_off[sid];
-    uint32_t cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t) cap64;
-    uint32_t rl = 0, st = 0;
-    inflate_stream(smem[warp_id()], comp + off[sid], len[sid], raw_out + raw_off[sid], cap, flags, rl, st);
-    if (lane_id() == 0) {
-        raw_len[sid] = rl;
-        status[sid] = st;
+    for (;;) {
+        uint32_t sid = 0;
+        if (lane_id() == 0) sid = atomicAdd(work_counter, 1u);
+        sid = __shfl_sync(ZWZ_FULL, sid, 0);
+        if (sid >= n) break;
+        uint64_t cap64 = raw_off[sid + 1] - raw_off[sid];
+        uint32_t cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t) cap64;
+        uint32_t rl = 0, st = 0;
+        inflate_stream(smem[warp_id()], comp + off[sid], len[sid], raw_out + raw_off[sid], cap, flags, rl, st);
+        if (lane_id() == 0) {
+            raw_len[sid] = rl;
+            status[sid] = st;
+        }
+        __syncwarp();
     }
 }
 

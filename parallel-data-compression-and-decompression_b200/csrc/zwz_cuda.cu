@@ -430,10 +430,10 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         }
         if ((rc = check_launch(ctx, "lz_match_kernel"))) return rc;
         ctx->launches--; // check_launch counted one more
-        uint32_t grid2 = (job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS;
+        uint32_t grid2 = std::min<uint32_t>((job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS, (uint32_t) ctx->sm_count * 8u);
         {
             ProfSpan ps(ctx, ZWZ_PROF_ENCODE, st);
-            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job);
+            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job, d_counters + 3);
         }
         if ((rc = check_launch(ctx, "deflate_encode_kernel"))) return rc;
     }
@@ -587,7 +587,7 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     const size_t r_base = align_up(meta_bytes, 256);
     int rc;
     if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 8), true))) return rc;
-    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 8 + 256, false))) return rc;
+    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 8 + 512, false))) return rc;
     uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
     memcpy(hp + m_off, off, (size_t) n * 8);
     memcpy(hp + m_roff, raw_off, (size_t) (n + 1) * 8);
@@ -596,10 +596,13 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint32_t *d_rlen = (uint32_t *) (dm + r_base);
     uint32_t *d_stat = d_rlen + n;
+    uint32_t *d_counter = d_stat + n; // work queue head of the persistent warps
+    if (zwz_rt::memset_device(d_counter, 0, 4, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
     {
         ProfSpan ps(ctx, ZWZ_PROF_INFLATE, st);
-        ZWZ_LAUNCH(zwz::inflate_kernel, (n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
-                   (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags);
+        uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * 8u);
+        ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
+                   (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags, d_counter);
     }
     if ((rc = check_launch(ctx, "inflate_kernel"))) return rc;
     if (zwz_rt::memcpy_d2h(hp, d_rlen, (size_t) n * 8, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "inflate kernel failed");
