@@ -536,21 +536,25 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
                 status = ZWZ_STREAM_BAD;
                 goto done;
             }
-            // copy: everything before `pos` must be in memory first
+            // copy: everything before `pos` must be in memory first. Loads go through L2 (ld.global.cg): the bytes were
+            // written by other lanes of this warp moments ago and L1 is not coherent for that.
             INF_FLUSH_LITS();
             __syncwarp();
             if (pos + mlen > cap) overflow = true;
-            if (dist >= 32u || dist >= mlen) {
+            if (mlen <= 32u && dist >= mlen) { // the common case: short, non-overlapping — one step, no loop
+                const uint32_t q = pos + lane;
+                if (lane < mlen && q < cap) out[q] = __ldcg(out + (q - dist));
+            } else if (dist >= 32u || dist >= mlen) {
                 for (uint32_t base = 0; base < mlen; base += 32u) { // warp-uniform trip count
                     uint32_t q = pos + base + lane;
-                    if (base + lane < mlen && q < cap) out[q] = ((volatile uint8_t *) out)[q - dist];
+                    if (base + lane < mlen && q < cap) out[q] = __ldcg(out + (q - dist));
                     __syncwarp(); // later steps may read what this step wrote (dist < mlen)
                 }
-            } else {
-                uint32_t src0 = pos - dist;
+            } else { // overlapping run with a period < 32: every byte comes from the already written period
+                const uint32_t src0 = pos - dist;
                 for (uint32_t i = lane; i < mlen; i += 32u) {
                     uint32_t q = pos + i;
-                    if (q < cap) out[q] = ((volatile uint8_t *) out)[src0 + (i % dist)];
+                    if (q < cap) out[q] = __ldcg(out + (src0 + (i % dist)));
                 }
             }
             __syncwarp();
