@@ -121,25 +121,42 @@ ZWZ_KERNEL md5_files_kernel(const uint8_t *__restrict__ data, const uint64_t *__
     uint32_t skew = (uint32_t) ((uintptr_t) p & 3u);
     const uint32_t *w = (const uint32_t *) (p - skew);
     uint32_t m[16];
+    // Software pipeline: the 64 bytes of block b+1 are loaded into registers before the 64 dependent steps of block b run,
+    // so the ~1 us of HBM latency of a lane's private stream hides behind ~1 100 cycles of arithmetic. (Lanes of a warp read 32
+    // different files: nothing coalesces, every block is two full 32-byte sectors per lane.)
     if (skew == 0) {
-        for (uint64_t b = 0; b < nblk; ++b) {
+        uint32_t nx[16];
+        if (nblk) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m[k] = __ldg(w + k);
-            md5_block(st, m);
-            w += 16;
+            for (int k = 0; k < 16; ++k) nx[k] = __ldg(w + k);
         }
-    } else {
-        uint32_t sh = skew * 8u;
-        uint32_t carry = nblk ? __ldg(w) : 0u;
         for (uint64_t b = 0; b < nblk; ++b) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                uint32_t nx = __ldg(w + k + 1); // word 16 of the block holds >= 1 valid byte because skew != 0
-                m[k] = __funnelshift_r(carry, nx, sh);
-                carry = nx;
+            for (int k = 0; k < 16; ++k) m[k] = nx[k];
+            w += 16;
+            if (b + 1 < nblk) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) nx[k] = __ldg(w + k);
             }
             md5_block(st, m);
+        }
+    } else {
+        const uint32_t sh = skew * 8u;
+        uint32_t nx[17];
+        if (nblk) {
+#pragma unroll
+            for (int k = 0; k < 17; ++k) nx[k] = __ldg(w + k); // word 16 of a block holds >= 1 valid byte because skew != 0
+        }
+        for (uint64_t b = 0; b < nblk; ++b) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[k] = __funnelshift_r(nx[k], nx[k + 1], sh);
             w += 16;
+            if (b + 1 < nblk) {
+                nx[0] = nx[16];
+#pragma unroll
+                for (int k = 1; k < 17; ++k) nx[k] = __ldg(w + k);
+            }
+            md5_block(st, m);
         }
     }
     if (finalize) {

@@ -81,8 +81,10 @@ class Compressor {
             return;
         }
         if (used_ + size > cap_ || files_.size() >= 262144) flush();
+        double t0 = now_seconds();
         size_t got = size ? std::fread(stage_ + used_, 1, size, f) : 0;
         std::fclose(f);
+        stats().t_read += now_seconds() - t0;
         files_.push_back({relpath, used_, got});
         used_ += got;
     }
@@ -98,8 +100,11 @@ class Compressor {
         std::vector<zwz_deflate_result> res(nc);
         std::vector<uint8_t> digest((size_t) nf * 16);
         ensure_out(used_ + nc * 64 + 4096);
+        double t0 = now_seconds();
         int rc = zwz_compress_files(ctx_, stage_, foff.data(), nf, level_, out_, out_cap_, poff.data(), res.data(), digest.data());
         if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_compress_files: ") + zwz_last_error(ctx_));
+        stats().t_gpu += now_seconds() - t0;
+        t0 = now_seconds();
         records_.clear();
         size_t c = 0;
         for (uint32_t i = 0; i < nf; ++i) {
@@ -113,6 +118,7 @@ class Compressor {
             if (config().verbose) std::cout << "md5 value size: " << MD5_DATA_SIZE << std::endl; // compression.cpp:100
         }
         write_out();
+        stats().t_write += now_seconds() - t0;
         files_.clear();
         used_ = 0;
     }
@@ -244,6 +250,7 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         std::cout << "Rank: " << world_rank << " - Total processed file: " << file_number << std::endl;
     }
     std::fclose(dest);
+    print_timing("compress");
 }
 
 } // namespace zwzhost

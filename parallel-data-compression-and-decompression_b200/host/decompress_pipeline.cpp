@@ -206,12 +206,14 @@ void big_file(zwz_ctx *ctx, const std::vector<uint8_t> &arch, FileState &fsx, co
 void decompress_zwz(const std::string &filename, const std::string &output_dir) {
     const RunConfig &cfg = config();
     std::vector<uint8_t> arch;
+    double t0 = now_seconds();
     if (!read_whole(filename, arch)) {
         std::cerr << "Error opening file: " << filename << std::endl;
         return;
     }
     std::vector<FileState> files;
     parse_archive(arch, files);
+    stats().t_read += now_seconds() - t0;
     zwz_ctx *ctx = ctx_for(cfg.device);
 
     // groups of whole files, bounded by the raw bytes they may produce
@@ -244,6 +246,7 @@ void decompress_zwz(const std::string &filename, const std::string &output_dir) 
                 ++k;
             }
         std::vector<uint8_t> digest((size_t) nf * 16);
+        t0 = now_seconds();
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
@@ -259,6 +262,8 @@ void decompress_zwz(const std::string &filename, const std::string &output_dir) 
                 }
             if (!again || attempt >= 2) break;
         }
+        stats().t_gpu += now_seconds() - t0;
+        t0 = now_seconds();
         for (size_t f = fi; f < fj; ++f) {
             FileState &fsx = files[f];
             std::string file_path = output_dir + "/" + fsx.relpath;
@@ -282,6 +287,7 @@ void decompress_zwz(const std::string &filename, const std::string &output_dir) 
                 print_verdict(file_path, fsx.stored_md5, std::string(hex, 32));
             }
         }
+        stats().t_write += now_seconds() - t0;
         fi = fj;
     }
 }
@@ -297,6 +303,7 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
     }
     std::sort(archives.begin(), archives.end());
     for (const auto &a : archives) decompress_zwz(a, output_dir);
+    print_timing("decompress");
 }
 
 } // namespace zwzhost

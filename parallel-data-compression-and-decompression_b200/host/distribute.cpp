@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdlib>
+#include <ctime>
 #include <fstream>
 #include <iostream>
 
@@ -21,6 +22,20 @@ RunConfig &config() {
 RunStats &stats() {
     static RunStats s;
     return s;
+}
+
+double now_seconds() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+void print_timing(const char *what) {
+    const char *e = std::getenv("ZWZ_TIMING");
+    if (!e || !*e || *e == '0') return;
+    const RunStats &s = stats();
+    std::cerr << "[zwz timing] " << what << ": init " << s.t_init << " s, read/parse " << s.t_read << " s, gpu passes " << s.t_gpu
+              << " s, write " << s.t_write << " s; " << s.files << " files, " << s.records << " records, " << s.raw_bytes << " raw bytes"
+              << std::endl;
 }
 
 static int env_int(const char *name, int dflt) {

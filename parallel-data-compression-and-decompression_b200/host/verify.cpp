@@ -18,7 +18,9 @@ zwz_ctx *ctx_for(int device) {
     auto it = all.find(device);
     if (it != all.end()) return it->second;
     zwz_ctx *c = nullptr;
+    double t0 = now_seconds();
     int rc = zwz_init(device, &c);
+    stats().t_init += now_seconds() - t0;
     if (rc != ZWZ_OK || !c) {
         std::cerr << "zwz: cannot initialise CUDA device " << device << " (error " << rc << "); there is no CPU fallback" << std::endl;
         throw std::runtime_error("zwz_init failed");

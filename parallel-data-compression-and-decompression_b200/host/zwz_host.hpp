@@ -47,7 +47,10 @@ std::vector<FileEntry> collect_and_sort(const std::filesystem::path &path);
 
 struct RunStats {
     uint64_t files = 0, records = 0, raw_bytes = 0, payload_bytes = 0, md5_match = 0, md5_mismatch = 0;
+    double t_read = 0, t_gpu = 0, t_write = 0, t_init = 0; // seconds, printed with ZWZ_TIMING=1
 };
+double now_seconds();
+void print_timing(const char *what);
 RunStats &stats();
 
 } // namespace zwzhost

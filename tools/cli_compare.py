@@ -97,11 +97,14 @@ def main():
         import torch
         ngpu = max(1, torch.cuda.device_count())
         our_ranks = min(a.ranks, ngpu)
-        t, _ = run_ranks(MAIN, ["compress", src, our_arch], our_ranks, lambda r: {"ZWZ_WORLD": str(our_ranks), "ZWZ_RANK": str(r)})
+        t, outs = run_ranks(MAIN, ["compress", src, our_arch], our_ranks,
+                            lambda r: {"ZWZ_WORLD": str(our_ranks), "ZWZ_RANK": str(r), "ZWZ_TIMING": "1"})
         res["our_compress_s"], res["our_ranks"] = t, our_ranks
+        res["our_compress_phases"] = [l for o in outs for l in o.splitlines() if "[zwz timing]" in l]
         our_out = os.path.join(tmp, "our_out")
-        t, outs = run_ranks(MAIN, ["decompress", our_arch, our_out], 1, lambda r: {})
+        t, outs = run_ranks(MAIN, ["decompress", our_arch, our_out], 1, lambda r: {"ZWZ_TIMING": "1"})
         res["our_decompress_s"] = t
+        res["our_decompress_phases"] = [l for o in outs for l in o.splitlines() if "[zwz timing]" in l]
         res["our_archive_bytes"] = du(our_arch)
         res["our_verdicts"] = {"match": outs[0].count("MD5 match for file"), "mismatch": outs[0].count("MD5 mismatch for file")}
         ok, n = same_tree(src, our_out)
