@@ -376,7 +376,8 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
             uint32_t k0 = k;
             for (uint32_t i = b; i < e; ++i)
                 if (len[i] >= lo_len && len[i] <= hi_len) o[k++] = i - b;
-            std::stable_sort(o + k0, o + k, [&](uint32_t x, uint32_t y) { return len[b + x] > len[b + y]; });
+            auto longer = [&](uint32_t x, uint32_t y) { return len[b + x] > len[b + y]; };
+            if (!std::is_sorted(o + k0, o + k, longer)) std::stable_sort(o + k0, o + k, longer); // size-sorted shards (the reference's deal) skip this
         }
         cls_begin[s * 4 + 3] = k;
     }
