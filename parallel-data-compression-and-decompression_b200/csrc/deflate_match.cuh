@@ -21,13 +21,14 @@
 //      coalesced); the parse in deflate_encode.cuh picks the path through them;
 //   6. Adler-32 of the chunk is reduced from shared memory while it is there.
 //
-// Three size classes so that small chunks do not leave an SM to one serial chain builder (config C2 is 370 000 chunks of
+// Four size classes so that small chunks do not leave an SM to one serial chain builder (config C2 is 370 000 chunks of
 // ~6.7 KB): the class fixes the shared-memory footprint and with it how many CTAs — each with its own builder warp — an SM
 // holds.
 //      class   chunk bytes   threads   smem/CTA   CTAs/SM   hash bits
-//        S       <=  8 192      256     ~33 KB       6         12
-//        M       <= 32 768      512    ~113 KB       2         13
-//        L       <= 65 535     1024    ~225 KB       1         14
+//        0       <=  8 192      256     ~33 KB       6         12
+//        1       <= 16 384      512     ~58 KB       3         12
+//        2       <= 32 768      512    ~114 KB       2         13
+//        3       <= 65 535     1024    ~227 KB       1         14
 // Algorithmic HBM bytes per chunk for the roofline: N_raw read (the 4 N_raw scratch write is traffic of this design, not of
 // the algorithm — reported separately in DESIGN.md).
 #pragma once
@@ -43,10 +44,14 @@ template <> struct MatchClass<0> {
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 8u * 8u;
 };
 template <> struct MatchClass<1> {
-    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64, kListBits = 4;
+    static constexpr uint32_t kCap = 16384, kThreads = 512, kHBits = 12, kData = 16384 + 64, kListBits = 4;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<2> {
+    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64, kListBits = 4;
+    static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
+};
+template <> struct MatchClass<3> {
     static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600, kListBits = 5;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 640u + 2u * 32u * 32u;
 };

@@ -199,10 +199,11 @@ int zwz_init(int device, zwz_ctx **out) {
         return ZWZ_E_NODEVICE;
     }
 #endif
-    if (ctx->smem_optin < zwz::MatchClass<2>::kSmem || zwz_rt::stream_create(&ctx->stream) ||
+    if (ctx->smem_optin < zwz::MatchClass<3>::kSmem || zwz_rt::stream_create(&ctx->stream) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<0>, zwz::MatchClass<0>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<1>, zwz::MatchClass<1>::kSmem) ||
-        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem)) {
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<3>, zwz::MatchClass<3>::kSmem)) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
@@ -365,24 +366,25 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
     // size classes (deflate_match.cuh): per sub-batch, chunk indices grouped by class, longest first inside a class so the
     // persistent CTAs end together
     const size_t nsub = sub_begin.size() - 1;
-    std::vector<uint32_t> cls_begin(nsub * 4);
+    std::vector<uint32_t> cls_begin(nsub * 5);
     for (size_t s = 0; s < nsub; ++s) {
         uint32_t b = sub_begin[s], e = sub_begin[s + 1];
         uint32_t *o = h_order + b;
         uint32_t k = 0;
-        for (int cls = 0; cls < 3; ++cls) {
-            cls_begin[s * 4 + cls] = k;
-            uint32_t lo_len = cls == 0 ? 0u : (cls == 1 ? 8193u : 32769u), hi_len = cls == 0 ? 8192u : (cls == 1 ? 32768u : 65535u);
+        static const uint32_t kClassHi[4] = {8192u, 16384u, 32768u, 65535u};
+        for (int cls = 0; cls < 4; ++cls) {
+            cls_begin[s * 5 + cls] = k;
+            uint32_t lo_len = cls == 0 ? 0u : kClassHi[cls - 1] + 1u, hi_len = kClassHi[cls];
             uint32_t k0 = k;
             for (uint32_t i = b; i < e; ++i)
                 if (len[i] >= lo_len && len[i] <= hi_len) o[k++] = i - b;
             auto longer = [&](uint32_t x, uint32_t y) { return len[b + x] > len[b + y]; };
             if (!std::is_sorted(o + k0, o + k, longer)) std::stable_sort(o + k0, o + k, longer); // size-sorted shards (the reference's deal) skip this
         }
-        cls_begin[s * 4 + 3] = k;
+        cls_begin[s * 5 + 4] = k;
     }
-    if ((rc = reserve(ctx, ctx->counter, nsub * 16 + 256, false))) return rc;
-    if (zwz_rt::memset_device(ctx->counter.p, 0, nsub * 16, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
+    if ((rc = reserve(ctx, ctx->counter, nsub * 32 + 256, false))) return rc;
+    if (zwz_rt::memset_device(ctx->counter.p, 0, nsub * 32, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
 
     uint8_t *dm = (uint8_t *) ctx->meta.p;
     if (zwz_rt::memcpy_h2d(dm, ctx->pin_meta.p, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
@@ -409,23 +411,24 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         job.nice = lp.nice;
         job.work_counter = nullptr;
         const uint32_t *d_order = (const uint32_t *) ((const uint64_t *) dm + 3 * (size_t) n) + n + b;
-        uint32_t *d_counters = (uint32_t *) ctx->counter.p + s * 4;
-        for (int cls = 0; cls < 3; ++cls) {
-            uint32_t w0 = cls_begin[s * 4 + cls], w1 = cls_begin[s * 4 + cls + 1];
+        uint32_t *d_counters = (uint32_t *) ctx->counter.p + s * 8; // [0..3] match classes, [4] encoder
+        for (int cls = 0; cls < 4; ++cls) {
+            uint32_t w0 = cls_begin[s * 5 + cls], w1 = cls_begin[s * 5 + cls + 1];
             if (w1 == w0) continue;
             ProfSpan ps(ctx, ZWZ_PROF_MATCH, st);
+            const uint32_t nwork = w1 - w0, sms = (uint32_t) ctx->sm_count;
             if (cls == 0) {
-                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count * 6u);
-                ZWZ_LAUNCH(zwz::lz_match_kernel<0>, grid, zwz::MatchClass<0>::kThreads, zwz::MatchClass<0>::kSmem, st, job, d_order + w0, w1 - w0,
-                           d_counters + cls);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<0>, std::min(nwork, sms * 6u), zwz::MatchClass<0>::kThreads, zwz::MatchClass<0>::kSmem, st, job,
+                           d_order + w0, nwork, d_counters + cls);
             } else if (cls == 1) {
-                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count * 2u);
-                ZWZ_LAUNCH(zwz::lz_match_kernel<1>, grid, zwz::MatchClass<1>::kThreads, zwz::MatchClass<1>::kSmem, st, job, d_order + w0, w1 - w0,
-                           d_counters + cls);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<1>, std::min(nwork, sms * 3u), zwz::MatchClass<1>::kThreads, zwz::MatchClass<1>::kSmem, st, job,
+                           d_order + w0, nwork, d_counters + cls);
+            } else if (cls == 2) {
+                ZWZ_LAUNCH(zwz::lz_match_kernel<2>, std::min(nwork, sms * 2u), zwz::MatchClass<2>::kThreads, zwz::MatchClass<2>::kSmem, st, job,
+                           d_order + w0, nwork, d_counters + cls);
             } else {
-                uint32_t grid = std::min<uint32_t>(w1 - w0, (uint32_t) ctx->sm_count);
-                ZWZ_LAUNCH(zwz::lz_match_kernel<2>, grid, zwz::MatchClass<2>::kThreads, zwz::MatchClass<2>::kSmem, st, job, d_order + w0, w1 - w0,
-                           d_counters + cls);
+                ZWZ_LAUNCH(zwz::lz_match_kernel<3>, std::min(nwork, sms), zwz::MatchClass<3>::kThreads, zwz::MatchClass<3>::kSmem, st, job,
+                           d_order + w0, nwork, d_counters + cls);
             }
             ctx->launches++;
         }
@@ -434,7 +437,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         uint32_t grid2 = std::min<uint32_t>((job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS, (uint32_t) ctx->sm_count * 8u);
         {
             ProfSpan ps(ctx, ZWZ_PROF_ENCODE, st);
-            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job, d_counters + 3);
+            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job, d_counters + 4);
         }
         if ((rc = check_launch(ctx, "deflate_encode_kernel"))) return rc;
     }
