@@ -30,6 +30,7 @@ namespace zwz {
 #define ZWZ_DE_LL 286
 #define ZWZ_DE_D 30
 #define ZWZ_DE_DOFF 288 // distance symbols live at freq[288 + d]
+#define ZWZ_DE_BASE 4096u // tokens per base block (blocks are merged runs of these)
 
 struct EncWarpSmem {
     uint32_t freq[320];     // [0,286) literal/length, [288,318) distance
@@ -196,15 +197,17 @@ ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, ui
 // bit sink: warp-collective append of (bits, nbits <= 57) per lane, in lane order
 // -------------------------------------------------------------------------------------------------------------------
 struct BitSink {
-    uint32_t *outw;    // 4-byte aligned output words
-    uint32_t nwords;   // words already stored
-    uint32_t fill;     // bits waiting in stage[0]
+    uint32_t *outw;     // 4-byte aligned output words
+    uint32_t nwords;    // words already produced (counted even when they no longer fit)
+    uint32_t fill;      // bits waiting in stage[0]
+    uint32_t cap_words; // words the output slot can take; past it the sink only counts
 };
 
-ZWZ_DEV void sink_init(EncWarpSmem &S, BitSink &k, uint32_t *outw) {
+ZWZ_DEV void sink_init(EncWarpSmem &S, BitSink &k, uint32_t *outw, uint32_t cap_words) {
     k.outw = outw;
     k.nwords = 0;
     k.fill = 0;
+    k.cap_words = cap_words;
     S.stage[lane_id()] = 0;
     S.stage[lane_id() + 32u] = 0;
     __syncwarp();
@@ -226,8 +229,8 @@ ZWZ_DEV void sink_put(EncWarpSmem &S, BitSink &k, uint64_t bits, uint32_t nbits)
     uint32_t nf = k.fill + total;
     uint32_t full = nf >> 5;
     uint32_t v0 = S.stage[lane], v1 = S.stage[lane + 32u];
-    if (lane < full) k.outw[k.nwords + lane] = v0;
-    if (lane + 32u < full) k.outw[k.nwords + lane + 32u] = v1;
+    if (lane < full && k.nwords + lane < k.cap_words) k.outw[k.nwords + lane] = v0;
+    if (lane + 32u < full && k.nwords + lane + 32u < k.cap_words) k.outw[k.nwords + lane + 32u] = v1;
     uint32_t carry = __shfl_sync(ZWZ_FULL, full < 32u ? v0 : v1, (int) (full & 31u));
     __syncwarp();
     S.stage[lane] = lane == 0 ? carry : 0u;
@@ -236,9 +239,9 @@ ZWZ_DEV void sink_put(EncWarpSmem &S, BitSink &k, uint64_t bits, uint32_t nbits)
     k.nwords += full;
     k.fill = nf & 31u;
 }
-// store the partial last word; returns total bytes
+// store the partial last word; returns total bytes (may exceed the slot: then nothing past it was written)
 ZWZ_DEV uint32_t sink_finish(EncWarpSmem &S, BitSink &k) {
-    if (k.fill && lane_id() == 0) k.outw[k.nwords] = S.stage[0];
+    if (k.fill && lane_id() == 0 && k.nwords < k.cap_words) k.outw[k.nwords] = S.stage[0];
     return k.nwords * 4u + ((k.fill + 7u) >> 3);
 }
 
@@ -275,6 +278,227 @@ ZWZ_DEV uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, uint32_t n,
     }
     for (uint32_t i = lane; i < n; i += 32u) out[7u + i] = src[i];
     return n + 11u;
+}
+
+// histogram of the tokens [t0, t1) into freq[0..320) (literal/length at 0, distance at 288); returns their extra bits
+ZWZ_DEV uint64_t enc_hist_tokens(const uint32_t *m, uint32_t t0, uint32_t t1, uint32_t *freq) {
+    const unsigned lane = lane_id();
+    for (uint32_t i = lane; i < 320u; i += 32u) freq[i] = 0;
+    __syncwarp();
+    uint64_t extra = 0;
+    for (uint32_t i = t0 + lane; i < t1; i += 32u) {
+        uint32_t tok = m[i];
+        uint32_t len = tok >> 16;
+        if (len == 0u) {
+            atomicAdd(&freq[tok], 1u);
+        } else {
+            uint32_t ls, le, lv, ds, de, dv;
+            len_symbol(len, ls, le, lv);
+            dist_symbol(tok & 0xffffu, ds, de, dv);
+            atomicAdd(&freq[ls], 1u);
+            atomicAdd(&freq[ZWZ_DE_DOFF + ds], 1u);
+            extra += le + de;
+        }
+    }
+    extra = warp_sum64(extra);
+    __syncwarp();
+    return extra;
+}
+
+// empirical entropy (bits) of the two alphabets in a[0..320) (+ b[0..320) when b != nullptr), and the used-symbol count
+ZWZ_DEV float enc_entropy_bits(const uint32_t *a, const uint32_t *b, uint32_t &nused_out) {
+    const unsigned lane = lane_id();
+    float nl = 0.f, nd = 0.f, h = 0.f;
+    uint32_t nused = 0;
+    for (uint32_t s = lane; s < 320u; s += 32u) {
+        float f = (float) (a[s] + (b ? b[s] : 0u));
+        if (s < ZWZ_DE_DOFF) nl += f; else nd += f;
+        nused += f > 0.f ? 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nl += __shfl_xor_sync(ZWZ_FULL, nl, d);
+        nd += __shfl_xor_sync(ZWZ_FULL, nd, d);
+    }
+    for (uint32_t s = lane; s < 320u; s += 32u) {
+        float f = (float) (a[s] + (b ? b[s] : 0u));
+        if (f > 0.f) h += f * (zwz_log2f(s < ZWZ_DE_DOFF ? nl : nd) - zwz_log2f(f));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(ZWZ_FULL, h, d);
+    nused_out = warp_sum(nused);
+    return h;
+}
+
+// One DEFLATE block over the tokens [t0, t1): S.freq must hold their histogram (without the end-of-block symbol).
+// Builds the three Huffman codes, picks fixed or dynamic (whichever is smaller) and appends the block to the sink.
+ZWZ_DEV void enc_emit_block(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint32_t t0, uint32_t t1, uint64_t extra_bits, bool last) {
+    const unsigned lane = lane_id();
+    if (lane == 0) S.freq[256] += 1u; // end of block
+    __syncwarp();
+    enc_huffman(S, S.freq, ZWZ_DE_LL, 15u, S.blen, S.code);
+    enc_huffman(S, S.freq + ZWZ_DE_DOFF, ZWZ_DE_D, 15u, S.blen + ZWZ_DE_DOFF, S.code + ZWZ_DE_DOFF);
+    __syncwarp();
+
+    // HLIT / HDIST: highest used symbol + 1
+    uint32_t hl = 0, hd = 0;
+    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u)
+        if (S.blen[s]) hl = s + 1u;
+    if (lane < ZWZ_DE_D && S.blen[ZWZ_DE_DOFF + lane]) hd = lane + 1u;
+    hl = warp_max(hl);
+    hd = warp_max(hd);
+    if (hl < 257u) hl = 257u;
+    if (hd < 1u) hd = 1u;
+
+    // code-length run-length coding (RFC 1951 §3.2.7; same run rules as zlib's scan_tree)
+    if (lane < 20u) S.clfreq[lane] = 0;
+    __syncwarp();
+    uint32_t ncl = 0;
+    if (lane == 0) {
+        for (int part = 0; part < 2; ++part) {
+            const uint8_t *L = part == 0 ? S.blen : S.blen + ZWZ_DE_DOFF;
+            uint32_t cnt_syms = part == 0 ? hl : hd;
+            int prevlen = -1;
+            uint32_t i = 0;
+            while (i < cnt_syms) {
+                uint32_t cur = L[i];
+                uint32_t run = 1;
+                uint32_t maxrun = cur == 0u ? 138u : ((int) cur == prevlen ? 6u : 7u);
+                while (i + run < cnt_syms && L[i + run] == cur && run < maxrun) ++run;
+                uint32_t minrun = cur == 0u ? 3u : ((int) cur == prevlen ? 3u : 4u);
+                if (run < minrun) {
+                    for (uint32_t r = 0; r < run; ++r) {
+                        S.cl_sym[ncl] = (uint8_t) cur;
+                        S.cl_ext[ncl++] = 0;
+                    }
+                    S.clfreq[cur] += run;
+                } else if (cur != 0u) {
+                    uint32_t rep = run;
+                    if ((int) cur != prevlen) {
+                        S.cl_sym[ncl] = (uint8_t) cur;
+                        S.cl_ext[ncl++] = 0;
+                        S.clfreq[cur] += 1u;
+                        rep = run - 1u;
+                    }
+                    S.cl_sym[ncl] = 16;
+                    S.cl_ext[ncl++] = (uint8_t) (rep - 3u);
+                    S.clfreq[16] += 1u;
+                } else if (run <= 10u) {
+                    S.cl_sym[ncl] = 17;
+                    S.cl_ext[ncl++] = (uint8_t) (run - 3u);
+                    S.clfreq[17] += 1u;
+                } else {
+                    S.cl_sym[ncl] = 18;
+                    S.cl_ext[ncl++] = (uint8_t) (run - 11u);
+                    S.clfreq[18] += 1u;
+                }
+                prevlen = (int) cur;
+                i += run;
+            }
+        }
+        S.misc[0] = ncl;
+    }
+    __syncwarp();
+    ncl = S.misc[0];
+    enc_huffman(S, S.clfreq, 19u, 7u, S.clblen, S.clcode);
+    __syncwarp();
+    // HCLEN: last used entry in the transmission order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+    uint32_t ord = lane < 3u ? 16u + lane : (lane == 3u ? 0u : ((lane & 1u) ? 7u - ((lane - 5u) >> 1) : 8u + ((lane - 4u) >> 1)));
+    uint32_t hc = (lane < 19u && S.clblen[ord]) ? lane + 1u : 0u;
+    hc = warp_max(hc);
+    if (hc < 4u) hc = 4u;
+
+    // sizes of the two Huffman encodings of this block
+    uint64_t dyn_bits = 0, fix_bits = 0, hdr_bits = 0;
+    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u) {
+        uint32_t f = S.freq[s];
+        dyn_bits += (uint64_t) f * S.blen[s];
+        fix_bits += (uint64_t) f * (s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u)));
+    }
+    if (lane < ZWZ_DE_D) {
+        uint32_t f = S.freq[ZWZ_DE_DOFF + lane];
+        dyn_bits += (uint64_t) f * S.blen[ZWZ_DE_DOFF + lane];
+        fix_bits += (uint64_t) f * 5u;
+    }
+    if (lane < 19u) hdr_bits += (uint64_t) S.clfreq[lane] * (S.clblen[lane] + (lane == 16u ? 2u : (lane == 17u ? 3u : (lane == 18u ? 7u : 0u))));
+    dyn_bits = warp_sum64(dyn_bits) + extra_bits + warp_sum64(hdr_bits) + 14u + 3u * hc;
+    fix_bits = warp_sum64(fix_bits) + extra_bits;
+    const bool fixed = fix_bits <= dyn_bits;
+    const uint64_t bfinal = last ? 1u : 0u;
+
+    if (fixed) {
+        // fixed codes (RFC 1951 §3.2.6) into the same code[] layout
+        for (uint32_t s = lane; s < 288u; s += 32u) {
+            uint32_t L = s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u));
+            uint32_t cw = s < 144u ? 0x30u + s : (s < 256u ? 0x190u + (s - 144u) : (s < 280u ? s - 256u : 0xC0u + (s - 280u)));
+            if (s < ZWZ_DE_LL) S.code[s] = (L << 16) | (__brev(cw) >> (32u - L));
+        }
+        if (lane < ZWZ_DE_D) S.code[ZWZ_DE_DOFF + lane] = (5u << 16) | (__brev(lane) >> 27);
+        __syncwarp();
+        sink_put(S, k, lane == 0 ? (bfinal | (1ull << 1)) : 0ull, lane == 0 ? 3u : 0u);
+    } else {
+        // BFINAL, BTYPE=10, HLIT, HDIST, HCLEN, then HCLEN 3-bit lengths (lanes 1..19)
+        uint64_t v = 0;
+        uint32_t nb = 0;
+        if (lane == 0) {
+            v = bfinal | (2ull << 1) | ((uint64_t) (hl - 257u) << 3) | ((uint64_t) (hd - 1u) << 8) | ((uint64_t) (hc - 4u) << 13);
+            nb = 17u;
+        } else if (lane <= hc) {
+            uint32_t o = lane - 1u;
+            uint32_t od = o < 3u ? 16u + o : (o == 3u ? 0u : ((o & 1u) ? 7u - ((o - 5u) >> 1) : 8u + ((o - 4u) >> 1)));
+            v = S.clblen[od];
+            nb = 3u;
+        }
+        sink_put(S, k, v, nb);
+        for (uint32_t base = 0; base < ncl; base += 32u) {
+            uint32_t i = base + lane;
+            uint64_t b = 0;
+            uint32_t nbits = 0;
+            if (i < ncl) {
+                uint32_t sy = S.cl_sym[i];
+                uint32_t cw = S.clcode[sy];
+                nbits = cw >> 16;
+                b = cw & 0xffffu;
+                uint32_t eb = sy == 16u ? 2u : (sy == 17u ? 3u : (sy == 18u ? 7u : 0u));
+                b |= (uint64_t) S.cl_ext[i] << nbits;
+                nbits += eb;
+            }
+            sink_put(S, k, b, nbits);
+        }
+    }
+    // tokens, then end-of-block
+    for (uint32_t base = t0; base <= t1; base += 32u) {
+        uint32_t i = base + lane;
+        uint64_t b = 0;
+        uint32_t nbits = 0;
+        if (i < t1) {
+            uint32_t tok = m[i];
+            uint32_t len = tok >> 16;
+            if (len == 0u) {
+                uint32_t cw = S.code[tok];
+                nbits = cw >> 16;
+                b = cw & 0xffffu;
+            } else {
+                uint32_t ls, le, lv, ds, de, dv;
+                len_symbol(len, ls, le, lv);
+                dist_symbol(tok & 0xffffu, ds, de, dv);
+                uint32_t cl = S.code[ls], cd = S.code[ZWZ_DE_DOFF + ds];
+                b = cl & 0xffffu;
+                nbits = cl >> 16;
+                b |= (uint64_t) lv << nbits;
+                nbits += le;
+                b |= (uint64_t) (cd & 0xffffu) << nbits;
+                nbits += cd >> 16;
+                b |= (uint64_t) dv << nbits;
+                nbits += de;
+            }
+        } else if (i == t1) {
+            uint32_t cw = S.code[256];
+            nbits = cw >> 16;
+            b = cw & 0xffffu;
+        }
+        sink_put(S, k, b, nbits);
+    }
 }
 
 ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
@@ -387,203 +611,67 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         return;
     }
 
-    // ---------------- codes ----------------
-    enc_huffman(S, S.freq, ZWZ_DE_LL, 15u, S.blen, S.code);
-    enc_huffman(S, S.freq + ZWZ_DE_DOFF, ZWZ_DE_D, 15u, S.blen + ZWZ_DE_DOFF, S.code + ZWZ_DE_DOFF);
-    __syncwarp();
-
-    // HLIT / HDIST: highest used symbol + 1
-    uint32_t hl = 0, hd = 0;
-    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u)
-        if (S.blen[s]) hl = s + 1u;
-    if (lane < ZWZ_DE_D && S.blen[ZWZ_DE_DOFF + lane]) hd = lane + 1u;
-    hl = warp_max(hl);
-    hd = warp_max(hd);
-    if (hl < 257u) hl = 257u;
-    if (hd < 1u) hd = 1u;
-
-    // ---------------- code-length run-length coding (RFC 1951 §3.2.7; same run rules as zlib's scan_tree) ----------------
-    if (lane < 20u) S.clfreq[lane] = 0;
-    __syncwarp();
-    uint32_t ncl = 0;
-    if (lane == 0) {
-        for (int part = 0; part < 2; ++part) {
-            const uint8_t *L = part == 0 ? S.blen : S.blen + ZWZ_DE_DOFF;
-            uint32_t cnt_syms = part == 0 ? hl : hd;
-            int prevlen = -1;
-            uint32_t i = 0;
-            while (i < cnt_syms) {
-                uint32_t cur = L[i];
-                uint32_t run = 1;
-                uint32_t maxrun = cur == 0u ? 138u : ((int) cur == prevlen ? 6u : 7u);
-                while (i + run < cnt_syms && L[i + run] == cur && run < maxrun) ++run;
-                uint32_t minrun = cur == 0u ? 3u : ((int) cur == prevlen ? 3u : 4u);
-                if (run < minrun) {
-                    for (uint32_t r = 0; r < run; ++r) {
-                        S.cl_sym[ncl] = (uint8_t) cur;
-                        S.cl_ext[ncl++] = 0;
-                    }
-                    S.clfreq[cur] += run;
-                } else if (cur != 0u) {
-                    uint32_t rep = run;
-                    if ((int) cur != prevlen) {
-                        S.cl_sym[ncl] = (uint8_t) cur;
-                        S.cl_ext[ncl++] = 0;
-                        S.clfreq[cur] += 1u;
-                        rep = run - 1u;
-                    }
-                    S.cl_sym[ncl] = 16;
-                    S.cl_ext[ncl++] = (uint8_t) (rep - 3u);
-                    S.clfreq[16] += 1u;
-                } else if (run <= 10u) {
-                    S.cl_sym[ncl] = 17;
-                    S.cl_ext[ncl++] = (uint8_t) (run - 3u);
-                    S.clfreq[17] += 1u;
-                } else {
-                    S.cl_sym[ncl] = 18;
-                    S.cl_ext[ncl++] = (uint8_t) (run - 11u);
-                    S.clfreq[18] += 1u;
-                }
-                prevlen = (int) cur;
-                i += run;
-            }
-        }
-        S.misc[0] = ncl;
-    }
-    __syncwarp();
-    ncl = S.misc[0];
-    enc_huffman(S, S.clfreq, 19u, 7u, S.clblen, S.clcode);
-    __syncwarp();
-    // HCLEN: last used entry in the transmission order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
-    uint32_t ord = lane < 3u ? 16u + lane : (lane == 3u ? 0u : ((lane & 1u) ? 7u - ((lane - 5u) >> 1) : 8u + ((lane - 4u) >> 1)));
-    uint32_t hc = (lane < 19u && S.clblen[ord]) ? lane + 1u : 0u;
-    hc = warp_max(hc);
-    if (hc < 4u) hc = 4u;
-
-    // ---------------- sizes ----------------
-    uint64_t dyn_bits = 0, fix_bits = 0, hdr_bits = 0;
-    for (uint32_t s = lane; s < ZWZ_DE_LL; s += 32u) {
-        uint32_t f = S.freq[s];
-        dyn_bits += (uint64_t) f * S.blen[s];
-        fix_bits += (uint64_t) f * (s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u)));
-    }
-    if (lane < ZWZ_DE_D) {
-        uint32_t f = S.freq[ZWZ_DE_DOFF + lane];
-        dyn_bits += (uint64_t) f * S.blen[ZWZ_DE_DOFF + lane];
-        fix_bits += (uint64_t) f * 5u;
-    }
-    if (lane < 19u) hdr_bits += (uint64_t) S.clfreq[lane] * (S.clblen[lane] + (lane == 16u ? 2u : (lane == 17u ? 3u : (lane == 18u ? 7u : 0u))));
-    dyn_bits = warp_sum64(dyn_bits) + extra_bits;
-    fix_bits = warp_sum64(fix_bits) + extra_bits;
-    hdr_bits = warp_sum64(hdr_bits) + 14u + 3u * hc;
-    const uint64_t dyn_total = 3u + hdr_bits + dyn_bits;
-    const uint64_t fix_total = 3u + fix_bits;
-    const uint32_t dyn_bytes = (uint32_t) ((dyn_total + 7u) >> 3) + 6u;
-    const uint32_t fix_bytes = (uint32_t) ((fix_total + 7u) >> 3) + 6u;
-    uint32_t btype = 2u, best = dyn_bytes;
-    if (fix_bytes <= best) {
-        btype = 1u;
-        best = fix_bytes;
-    }
-    if (sto_bytes <= best + sto_slack) { // see the policy above
-        btype = 0u;
-        best = sto_bytes;
-    }
-
-    uint32_t len0 = 0, len1 = 0, raw0 = n;
-    const uint32_t adler = job.adler[c];
-    if (best > ZWZ_CHUNK) {
-        // split rule: two stored streams over the halves (each needs its own Adler-32)
-        raw0 = 32768u;
-        uint32_t a0 = enc_adler_global(src, raw0);
-        uint32_t a1 = enc_adler_global(src + raw0, n - raw0);
-        len0 = enc_stored_stream(out, src, raw0, a0);
-        len1 = enc_stored_stream(out + len0, src + raw0, n - raw0, a1);
-        btype = 0u;
-    } else if (btype == 0u) {
-        len0 = enc_stored_stream(out, src, n, adler);
+    // ---------------- blocks ----------------
+    // Base blocks of ZWZ_DE_BASE tokens are merged left to right while one Huffman code over the union is estimated (empirical
+    // entropy + a header estimate) to cost no more than two separate ones; a merged run becomes one DEFLATE block. zlib cuts
+    // every 16 383 symbols regardless of content; adapting the cut is worth several percent on data whose statistics drift
+    // (bitmap-like), nothing on homogeneous text.
+    const uint32_t cap_words = ((n + ZWZ_DEFLATE_MARGIN + 15u) & ~15u) >> 2; // zwz_deflate_bound(n) / 4
+    BitSink k;
+    sink_init(S, k, (uint32_t *) out, cap_words);
+    sink_put(S, k, lane == 0 ? 0x9c78ull : 0ull, lane == 0 ? 16u : 0u); // RFC 1950 header 78 9C
+    if (ntok <= ZWZ_DE_BASE) {
+        enc_emit_block(S, k, m, 0, ntok, extra_bits, true); // S.freq still holds the whole-chunk histogram from the parse
     } else {
-        BitSink k;
-        sink_init(S, k, (uint32_t *) out);
-        if (btype == 1u) {
-            // fixed codes (RFC 1951 §3.2.6) into the same code[] layout
-            for (uint32_t s = lane; s < 288u; s += 32u) {
-                uint32_t L = s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u));
-                uint32_t cw = s < 144u ? 0x30u + s : (s < 256u ? 0x190u + (s - 144u) : (s < 280u ? s - 256u : 0xC0u + (s - 280u)));
-                if (s < ZWZ_DE_LL) S.code[s] = (L << 16) | (__brev(cw) >> (32u - L));
-            }
-            if (lane < ZWZ_DE_D) S.code[ZWZ_DE_DOFF + lane] = (5u << 16) | (__brev(lane) >> 27);
-            __syncwarp();
-            sink_put(S, k, lane == 0 ? (0x9c78ull | (3ull << 16)) : 0ull, lane == 0 ? 19u : 0u);
-        } else {
-            // 78 9C, BFINAL=1 BTYPE=10, HLIT, HDIST, HCLEN, then HCLEN 3-bit lengths (lanes 1..19)
-            uint64_t v = 0;
-            uint32_t nb = 0;
-            if (lane == 0) {
-                v = 0x9c78ull | (5ull << 16) | ((uint64_t) (hl - 257u) << 19) | ((uint64_t) (hd - 1u) << 24) | ((uint64_t) (hc - 4u) << 29);
-                nb = 33u;
-            } else if (lane <= hc) {
-                uint32_t o = lane - 1u;
-                uint32_t od = o < 3u ? 16u + o : (o == 3u ? 0u : ((o & 1u) ? 7u - ((o - 5u) >> 1) : 8u + ((o - 4u) >> 1)));
-                v = S.clblen[od];
-                nb = 3u;
-            }
-            sink_put(S, k, v, nb);
-            for (uint32_t base = 0; base < ncl; base += 32u) {
-                uint32_t i = base + lane;
-                uint64_t b = 0;
-                uint32_t nbits = 0;
-                if (i < ncl) {
-                    uint32_t sy = S.cl_sym[i];
-                    uint32_t cw = S.clcode[sy];
-                    nbits = cw >> 16;
-                    b = cw & 0xffffu;
-                    uint32_t eb = sy == 16u ? 2u : (sy == 17u ? 3u : (sy == 18u ? 7u : 0u));
-                    b |= (uint64_t) S.cl_ext[i] << nbits;
-                    nbits += eb;
-                }
-                sink_put(S, k, b, nbits);
+        uint32_t t0 = 0, t1 = ZWZ_DE_BASE;
+        uint64_t xb = enc_hist_tokens(m, t0, t1, S.freq);
+        while (t1 < ntok) {
+            const uint32_t t2 = t1 + ZWZ_DE_BASE < ntok ? t1 + ZWZ_DE_BASE : ntok;
+            uint32_t *nf = S.code; // free until the next Huffman build
+            const uint64_t xn = enc_hist_tokens(m, t1, t2, nf);
+            uint32_t ua, ub, uab;
+            const float ha = enc_entropy_bits(S.freq, nullptr, ua);
+            const float hb = enc_entropy_bits(nf, nullptr, ub);
+            const float hab = enc_entropy_bits(S.freq, nf, uab);
+            const float sep = ha + hb + 200.f + 4.f * (float) (ua + ub);
+            const float mer = hab + 100.f + 4.f * (float) uab;
+            if (mer <= sep) {
+                for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] += nf[i];
+                __syncwarp();
+                xb += xn;
+                t1 = t2;
+            } else {
+                enc_emit_block(S, k, m, t0, t1, xb, false);
+                t0 = t1;
+                t1 = t2;
+                xb = enc_hist_tokens(m, t0, t1, S.freq);
             }
         }
-        // tokens, then end-of-block
-        for (uint32_t base = 0; base <= ntok; base += 32u) {
-            uint32_t i = base + lane;
-            uint64_t b = 0;
-            uint32_t nbits = 0;
-            if (i < ntok) {
-                uint32_t tok = m[i];
-                uint32_t len = tok >> 16;
-                if (len == 0u) {
-                    uint32_t cw = S.code[tok];
-                    nbits = cw >> 16;
-                    b = cw & 0xffffu;
-                } else {
-                    uint32_t dist = tok & 0xffffu ? (tok & 0xffffu) : 65536u;
-                    uint32_t ls, le, lv, ds, de, dv;
-                    len_symbol(len, ls, le, lv);
-                    dist_symbol(dist, ds, de, dv);
-                    uint32_t cl = S.code[ls], cd = S.code[ZWZ_DE_DOFF + ds];
-                    b = cl & 0xffffu;
-                    nbits = cl >> 16;
-                    b |= (uint64_t) lv << nbits;
-                    nbits += le;
-                    b |= (uint64_t) (cd & 0xffffu) << nbits;
-                    nbits += cd >> 16;
-                    b |= (uint64_t) dv << nbits;
-                    nbits += de;
-                }
-            } else if (i == ntok) {
-                uint32_t cw = S.code[256];
-                nbits = cw >> 16;
-                b = cw & 0xffffu;
-            }
-            sink_put(S, k, b, nbits);
-        }
-        // pad to a byte boundary, Adler-32 big-endian
+        enc_emit_block(S, k, m, t0, t1, xb, true);
+    }
+    // pad to a byte boundary, Adler-32 big-endian
+    const uint32_t adler = job.adler[c];
+    {
         uint32_t padbits = (8u - ((k.nwords * 32u + k.fill) & 7u)) & 7u;
         uint32_t be = ((adler & 0xffu) << 24) | ((adler & 0xff00u) << 8) | ((adler >> 8) & 0xff00u) | (adler >> 24);
         sink_put(S, k, lane == 1u ? (uint64_t) be : 0ull, lane == 0 ? padbits : (lane == 1u ? 32u : 0u));
-        len0 = sink_finish(S, k);
+    }
+    const uint32_t huff_bytes = sink_finish(S, k);
+    __syncwarp();
+
+    uint32_t len0 = huff_bytes, len1 = 0, raw0 = n, btype = 2u;
+    if (sto_bytes <= huff_bytes + sto_slack || huff_bytes > ZWZ_CHUNK || huff_bytes > cap_words * 4u) { // see the policy above
+        btype = 0u;
+        if (sto_bytes > ZWZ_CHUNK) {
+            // split rule: two stored streams over the halves (each needs its own Adler-32)
+            raw0 = 32768u;
+            uint32_t a0 = enc_adler_global(src, raw0);
+            uint32_t a1 = enc_adler_global(src + raw0, n - raw0);
+            len0 = enc_stored_stream(out, src, raw0, a0);
+            len1 = enc_stored_stream(out + len0, src + raw0, n - raw0, a1);
+        } else {
+            len0 = enc_stored_stream(out, src, n, adler);
+        }
     }
     if (lane == 0) {
         job.res[4u * c + 0u] = len0;
