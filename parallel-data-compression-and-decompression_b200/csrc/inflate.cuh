@@ -172,10 +172,9 @@ struct InfBits {
     uint32_t widx;          // next word to feed
     uint32_t cache, cache_next;
     uint32_t cache_blk;     // block (32 words) held in `cache`; cache_next holds cache_blk + 1
-    uint64_t hold;          // bits 0..63 of the bit buffer (bit 0 = next stream bit)
-    uint64_t hold1;         // bits 64..127
-    uint32_t cnt;           // valid bits in hold:hold1 (<= 128)
-    uint64_t fed;           // stream bits fed into the buffer so far (may run past 8 * nbytes: zero padding)
+    uint64_t hold;
+    uint32_t cnt;           // valid bits in hold
+    uint64_t fed;           // stream bits fed into hold so far (may run past 8 * nbytes: zero padding)
 };
 
 ZWZ_DEV uint32_t infb_load(const InfBits &b, uint32_t k) {
@@ -210,7 +209,6 @@ ZWZ_DEV void infb_seek(InfBits &b, uint32_t byte_pos) {
     b.widx = a >> 2;
     b.cache_blk = 0xfffffff0u;
     b.hold = 0;
-    b.hold1 = 0;
     b.cnt = 0;
     uint32_t w = infb_next_word(b);
     uint32_t drop = (a & 3u) * 8u;
@@ -218,28 +216,16 @@ ZWZ_DEV void infb_seek(InfBits &b, uint32_t byte_pos) {
     b.cnt = 32u - drop;
     b.fed = (uint64_t) byte_pos * 8u + b.cnt;
 }
-// top the 128-bit buffer up to more than 96 valid bits (a 32-offset decode window needs 31 + 48)
 ZWZ_DEV void infb_refill(InfBits &b) {
-    while (b.cnt <= 96u) { // warp-uniform
+    if (b.cnt <= 32u) {
         uint32_t w = infb_next_word(b);
-        if (b.cnt < 64u) {
-            b.hold |= (uint64_t) w << b.cnt;
-            if (b.cnt > 32u) b.hold1 |= (uint64_t) w >> (64u - b.cnt);
-        } else {
-            b.hold1 |= (uint64_t) w << (b.cnt - 64u);
-        }
+        b.hold |= (uint64_t) w << b.cnt;
         b.cnt += 32u;
         b.fed += 32u;
     }
 }
 ZWZ_DEV void infb_drop(InfBits &b, uint32_t n) {
-    if (n >= 64u) {
-        b.hold = n == 64u ? b.hold1 : b.hold1 >> (n - 64u);
-        b.hold1 = 0;
-    } else if (n) {
-        b.hold = (b.hold >> n) | (b.hold1 << (64u - n));
-        b.hold1 >>= n;
-    }
+    b.hold >>= n;
     b.cnt -= n;
 }
 // bits consumed from the stream so far
@@ -443,41 +429,24 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
 
         // ---- symbol loop ----
         for (;;) {
-            infb_refill(B); // > 96 valid bits
+            infb_refill(B); // >= 33 valid bits
+            uint32_t e;
             if (B.fed <= total_bits) {
-                // "Warp-ballot symbol decode": lane l decodes the COMPLETE symbol that would start at bit l of the buffer —
-                // a literal, or length code + extra bits + distance code + extra bits (<= 48 bits, two table look-ups). The
-                // ballot says which offsets hold a well-formed symbol; the offsets that really are symbol starts form the
-                // chain 0 -> nbits(0) -> ..., recovered with 5 rounds of pointer doubling on (reach mask, jump) pairs.
-                // Then the whole run is executed at once: a shuffle scan of the output lengths places every symbol, the
-                // literals are stored by their lanes, the matches are copied in chain order by the whole warp, and the
-                // run is dropped from the bit buffer in one shift. Anything unusual (code longer than the table index,
-                // end of block, invalid code, distance too far back, output capacity) ends the chain in front of it and goes
-                // through the one-symbol path below, which also owns the exact end-of-input semantics.
-                const uint64_t w = lane ? (B.hold >> lane) | (B.hold1 << (64u - lane)) : B.hold;
-                const uint32_t el = S.lit[(uint32_t) w & ((1u << ZWZ_INF_LBITS) - 1u)];
-                const uint32_t knd = (el >> 8) & 3u;
-                uint32_t nbits = el & 15u, olen = 1u, val = el >> 16, dist = 0u;
-                bool good = knd == INF_KIND_LIT;
-                if (knd == INF_KIND_BASE) {
-                    const uint32_t eb = (el >> 4) & 15u;
-                    val = (el >> 16) + ((uint32_t) (w >> nbits) & ((1u << eb) - 1u));
-                    nbits += eb;
-                    const uint32_t d = S.dst[(uint32_t) (w >> nbits) & ((1u << ZWZ_INF_DBITS) - 1u)];
-                    const uint32_t dnb = d & 15u, deb = (d >> 4) & 15u;
-                    dist = (d >> 16) + ((uint32_t) (w >> (nbits + dnb)) & ((1u << deb) - 1u));
-                    nbits += dnb + deb;
-                    olen = val;
-                    good = ((d >> 8) & 3u) == INF_KIND_BASE;
-                }
-                good = good && (lane + nbits <= B.cnt);
-                const unsigned goodmask = __ballot_sync(ZWZ_FULL, good);
-                if (goodmask & 1u) {
-                    uint32_t J = lane + nbits;
-                    uint32_t R = good ? (1u << lane) : 0u;
+                // Literal runs, 32 bit offsets at a time ("warp-ballot symbol decode"): lane l decodes the code that WOULD
+                // start at bit l of the buffer; the ballot says which offsets hold a complete literal; the offsets that
+                // really are code starts form the chain 0 -> nb(0) -> ..., recovered with 5 rounds of pointer doubling on
+                // (reach mask, jump) pairs. All literals on the chain are stored by their lanes in one go and the whole
+                // run is dropped from the bit buffer at once. The chain ends at the first non-literal (handled below) or
+                // past offset 31.
+                const uint32_t el = S.lit[(uint32_t) (B.hold >> lane) & ((1u << ZWZ_INF_LBITS) - 1u)];
+                const bool ok = (lane + 15u <= B.cnt) && ((el >> 8) & 3u) == INF_KIND_LIT;
+                const unsigned litmask = __ballot_sync(ZWZ_FULL, ok);
+                if (litmask & 1u) {
+                    uint32_t J = lane + (el & 15u);
+                    uint32_t R = ok ? (1u << lane) : 0u;
 #pragma unroll
                     for (int r = 0; r < 5; ++r) {
-                        const bool go = good && J < 32u && ((goodmask >> J) & 1u);
+                        const bool go = ok && J < 32u && ((litmask >> J) & 1u);
                         const int from = go ? (int) J : (int) lane;
                         const uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);
                         const uint32_t Jj = __shfl_sync(ZWZ_FULL, J, from);
@@ -488,44 +457,22 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
                     }
                     const uint32_t R0 = __shfl_sync(ZWZ_FULL, R, 0);
                     const uint32_t J0 = __shfl_sync(ZWZ_FULL, J, 0);
-                    const bool on = (R0 >> lane) & 1u;
-                    const uint32_t o = on ? olen : 0u;
-                    const uint32_t incl = warp_incl_scan(o);
-                    const uint32_t excl = incl - o;
-                    const uint32_t total = __shfl_sync(ZWZ_FULL, incl, 31);
-                    const bool is_match = on && dist != 0u;
-                    const unsigned far = __ballot_sync(ZWZ_FULL, is_match && dist > pos + excl);
-                    if (far == 0u && pos + total <= cap) {
-                        INF_FLUSH_LITS();
-                        if (on && dist == 0u) out[pos + excl] = (uint8_t) val;
-                        unsigned mm = __ballot_sync(ZWZ_FULL, is_match);
-                        __syncwarp();
-                        while (mm) { // matches of the run, in stream order (a later one may read what an earlier one wrote)
-                            const int L = __ffs((int) mm) - 1;
-                            mm &= mm - 1u;
-                            const uint32_t mlen = __shfl_sync(ZWZ_FULL, val, L);
-                            const uint32_t mdist = __shfl_sync(ZWZ_FULL, dist, L);
-                            const uint32_t q0 = pos + __shfl_sync(ZWZ_FULL, excl, L);
-                            if (mlen <= 32u && mdist >= mlen) {
-                                if (lane < mlen) out[q0 + lane] = __ldcg(out + (q0 + lane - mdist));
-                            } else if (mdist >= 32u || mdist >= mlen) {
-                                for (uint32_t base = 0; base < mlen; base += 32u) {
-                                    if (base + lane < mlen) out[q0 + base + lane] = __ldcg(out + (q0 + base + lane - mdist));
-                                    __syncwarp();
-                                }
-                            } else {
-                                for (uint32_t i = lane; i < mlen; i += 32u) out[q0 + i] = __ldcg(out + (q0 - mdist + (i % mdist)));
-                            }
-                            __syncwarp();
-                        }
-                        pos += total;
-                        pend_lo = pos;
-                        infb_drop(B, J0);
-                        continue;
+                    const uint32_t nlit = (uint32_t) __popc(R0);
+                    INF_FLUSH_LITS();
+                    if ((R0 >> lane) & 1u) {
+                        const uint32_t q = pos + (uint32_t) __popc(R0 & ((1u << lane) - 1u));
+                        if (q < cap) out[q] = (uint8_t) (el >> 16);
                     }
+                    if (pos + nlit > cap) overflow = true;
+                    pos += nlit;
+                    pend_lo = pos;
+                    infb_drop(B, J0);
+                    continue;
                 }
+                e = __shfl_sync(ZWZ_FULL, el, 0);
+            } else {
+                e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
             }
-            uint32_t e = S.lit[(uint32_t) B.hold & ((1u << ZWZ_INF_LBITS) - 1u)];
             uint32_t kind = (e >> 8) & 3u;
             uint32_t nb = e & 15u;
             if (kind == INF_KIND_SPECIAL) {
