@@ -511,6 +511,32 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] = 0;
     __syncwarp();
 
+    // ---------------- incompressibility shortcut ----------------
+    // The match kernel reports how many positions found a match. When (almost) none did, the token stream is (almost) the
+    // byte stream: its histogram comes straight from the raw bytes (coalesced, no dependent loads) and the entropy bound below
+    // decides "stored" without ever walking the 4-byte-per-position scratch. Config C2 is 70 % such chunks.
+    if (n >= 512u && job.nmatch[c] * 64u <= n) {
+        for (uint32_t i = lane; i < n; i += 32u) atomicAdd(&S.freq[src[i]], 1u);
+        __syncwarp();
+        if (lane == 0) S.freq[256] = 1u;
+        __syncwarp();
+        uint32_t nu;
+        const float hb = enc_entropy_bits(S.freq, nullptr, nu);
+        const float bound_bytes = hb * 0.125f + 7.f + (float) (nu >> 2);
+        if (bound_bytes * 0.9995f >= (float) (n + 11u) - (float) (n >> 8) && n + 11u <= ZWZ_CHUNK) {
+            uint32_t l0 = enc_stored_stream(out, src, n, job.adler[c]);
+            if (lane == 0) {
+                job.res[4u * c + 0u] = l0;
+                job.res[4u * c + 1u] = 0u;
+                job.res[4u * c + 2u] = n;
+                job.res[4u * c + 3u] = 0u;
+            }
+            return;
+        }
+        for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] = 0;
+        __syncwarp();
+    }
+
     // ---------------- parse ----------------
     uint32_t ntok = 0;
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)

@@ -61,6 +61,7 @@ struct MatchCtl {
     unsigned long long mbar;   // mbarrier for the bulk copy
     uint32_t next_tile;
     uint32_t cur_work;
+    uint32_t nmatch;           // positions of this chunk that found a match
     uint32_t base[33];         // list k = entries [base[k], base[k+1]) of the position list
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
@@ -141,7 +142,10 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
 #endif
         for (uint32_t i = tid; i < (1u << HB) / 2u; i += T) ((uint32_t *) head)[i] = 0xffffffffu;
         for (uint32_t i = tid; i < NW * NW / 2u; i += T) ((uint32_t *) cnt)[i] = 0u;
-        if (tid == 0) ctl->next_tile = 0;
+        if (tid == 0) {
+            ctl->next_tile = 0;
+            ctl->nmatch = 0;
+        }
 #ifndef ZWZ_EMU
         if (stage_bytes) dm_mbar_wait(&ctl->mbar, parity);
         parity ^= (stage_bytes != 0u);
@@ -314,6 +318,8 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             }
             if (p < n) mout[p] = best_len >= 3u ? ((best_len << 16) | best_dist) : 0u;
+            const unsigned hit = __ballot_sync(ZWZ_FULL, best_len >= 3u);
+            if (lane == 0 && hit) atomicAdd(&ctl->nmatch, (uint32_t) __popc(hit));
         }
         __syncthreads();
 
@@ -361,6 +367,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                     uint32_t a = (1u + part.a) % 65521u;
                     uint32_t b = (n % 65521u + part.b) % 65521u;
                     job.adler[c] = (b << 16) | a;
+                    job.nmatch[c] = ctl->nmatch;
                 }
             }
         }

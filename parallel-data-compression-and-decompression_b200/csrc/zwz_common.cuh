@@ -48,6 +48,7 @@ struct DeflateJob {
     const uint64_t *scr_off;   // [n]   offset (in uint32 units) of this chunk's match/token scratch
     uint32_t *scratch;         // 4 bytes per raw byte (+ pad)
     uint32_t *adler;           // [n]   written by the match kernel, read by the encoder
+    uint32_t *nmatch;          // [n]   positions that found a match (match kernel -> encoder: incompressibility shortcut)
     uint8_t *out;              // output slots
     const uint64_t *out_off;   // [n]   multiple of 4, capacity >= zwz_deflate_bound(len)
     uint32_t *res;             // [n*4] zwz_deflate_result

@@ -326,7 +326,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
 
     // descriptors: [raw_off u64][scr_off u64][out_off u64][raw_len u32][order u32] per chunk, then results + adler on the device
     const size_t meta_bytes = (size_t) n * (8 + 8 + 8 + 4 + 4);
-    const size_t dev_meta_bytes = align_up(meta_bytes, 256) + (size_t) n * 16 + (size_t) n * 4 + 256;
+    const size_t dev_meta_bytes = align_up(meta_bytes, 256) + (size_t) n * 16 + (size_t) n * 8 + 256;
     int rc;
     if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 16), true))) return rc;
     if ((rc = reserve(ctx, ctx->meta, dev_meta_bytes, false))) return rc;
@@ -390,6 +390,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
     if (zwz_rt::memcpy_h2d(dm, ctx->pin_meta.p, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint32_t *d_res = (uint32_t *) (dm + align_up(meta_bytes, 256));
     uint32_t *d_adler = d_res + (size_t) n * 4;
+    uint32_t *d_nmatch = d_adler + n;
     ctx->last_res_off = align_up(meta_bytes, 256);
     ctx->last_slot_off = 2 * (size_t) n * 8;
 
@@ -404,6 +405,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         job.raw_len = (const uint32_t *) ((const uint64_t *) dm + 3 * (size_t) n) + b;
         job.scratch = (uint32_t *) ctx->scratch.p;
         job.adler = d_adler + b;
+        job.nmatch = d_nmatch + b;
         job.out = d_out;
         job.res = d_res + (size_t) b * 4;
         job.n = e - b;
