@@ -99,20 +99,29 @@ ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, ui
     __syncwarp();
     for (uint32_t i = lane; i < nused; i += 32u) S.weight[i] = S.key[i] >> 9;
     __syncwarp();
-    // 3. two-queue merge (serial; the data is tiny and sorted, the other lanes wait)
+    // 3. two-queue merge (serial; the data is tiny and sorted, the other lanes wait). Queue heads live in registers.
     if (lane == 0) {
         uint32_t leaf = 0, inode = nused, next = nused;
         const uint32_t last = 2u * nused - 1u;
+        uint32_t wl = S.weight[0], wi = 0xffffffffu; // head weights; 0xffffffff = queue empty
         while (next < last) {
-            uint32_t pick[2];
+            uint32_t sum = 0;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                bool take_leaf = leaf < nused && (inode >= next || S.weight[leaf] <= S.weight[inode]);
-                pick[t] = take_leaf ? leaf++ : inode++;
+                if (wl <= wi) { // ties prefer the leaf (shallower trees)
+                    sum += wl;
+                    S.parent[leaf] = (uint16_t) next;
+                    ++leaf;
+                    wl = leaf < nused ? S.weight[leaf] : 0xffffffffu;
+                } else {
+                    sum += wi;
+                    S.parent[inode] = (uint16_t) next;
+                    ++inode;
+                    wi = inode < next ? S.weight[inode] : 0xffffffffu;
+                }
             }
-            S.weight[next] = S.weight[pick[0]] + S.weight[pick[1]];
-            S.parent[pick[0]] = (uint16_t) next;
-            S.parent[pick[1]] = (uint16_t) next;
+            S.weight[next] = sum;
+            if (wi == 0xffffffffu && inode == next) wi = sum; // the node just made becomes the internal head
             ++next;
         }
         S.parent[last - 1u] = 0xffffu; // root
@@ -646,13 +655,16 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     BitSink k;
     sink_init(S, k, (uint32_t *) out, cap_words);
     sink_put(S, k, lane == 0 ? 0x9c78ull : 0ull, lane == 0 ? 16u : 0u); // RFC 1950 header 78 9C
-    if (ntok <= ZWZ_DE_BASE) {
+    // base blocks of equal size, about ZWZ_DE_BASE tokens each (a short tail block would pay a whole header for nothing)
+    const uint32_t nbase = (ntok + ZWZ_DE_BASE / 2u) / ZWZ_DE_BASE;
+    if (nbase <= 1u) {
         enc_emit_block(S, k, m, 0, ntok, extra_bits, true); // S.freq still holds the whole-chunk histogram from the parse
     } else {
-        uint32_t t0 = 0, t1 = ZWZ_DE_BASE;
+        const uint32_t bsz = (ntok + nbase - 1u) / nbase;
+        uint32_t t0 = 0, t1 = bsz;
         uint64_t xb = enc_hist_tokens(m, t0, t1, S.freq);
         while (t1 < ntok) {
-            const uint32_t t2 = t1 + ZWZ_DE_BASE < ntok ? t1 + ZWZ_DE_BASE : ntok;
+            const uint32_t t2 = t1 + bsz < ntok ? t1 + bsz : ntok;
             uint32_t *nf = S.code; // free until the next Huffman build
             const uint64_t xn = enc_hist_tokens(m, t1, t2, nf);
             uint32_t ua, ub, uab;
