@@ -297,13 +297,13 @@ ZWZ_DEV uint64_t enc_hist_tokens(const uint32_t *m, uint32_t t0, uint32_t t1, ui
     uint64_t extra = 0;
     for (uint32_t i = t0 + lane; i < t1; i += 32u) {
         uint32_t tok = m[i];
-        uint32_t len = tok >> 16;
+        uint32_t len = tok_len(tok);
         if (len == 0u) {
-            atomicAdd(&freq[tok], 1u);
+            atomicAdd(&freq[tok_byte(tok)], 1u);
         } else {
             uint32_t ls, le, lv, ds, de, dv;
             len_symbol(len, ls, le, lv);
-            dist_symbol(tok & 0xffffu, ds, de, dv);
+            dist_symbol(tok_dist(tok), ds, de, dv);
             atomicAdd(&freq[ls], 1u);
             atomicAdd(&freq[ZWZ_DE_DOFF + ds], 1u);
             extra += le + de;
@@ -475,22 +475,25 @@ ZWZ_DEV void enc_emit_block(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint3
             sink_put(S, k, b, nbits);
         }
     }
-    // tokens, then end-of-block
+    // tokens, then end-of-block. The next step's token is loaded before this step's bits go through the sink (whose warp
+    // barriers the compiler will not move loads across).
+    uint32_t tnext = t0 + lane < t1 ? m[t0 + lane] : 0u;
     for (uint32_t base = t0; base <= t1; base += 32u) {
-        uint32_t i = base + lane;
+        const uint32_t i = base + lane;
+        const uint32_t tok = tnext;
+        tnext = i + 32u < t1 ? m[i + 32u] : 0u;
         uint64_t b = 0;
         uint32_t nbits = 0;
         if (i < t1) {
-            uint32_t tok = m[i];
-            uint32_t len = tok >> 16;
+            uint32_t len = tok_len(tok);
             if (len == 0u) {
-                uint32_t cw = S.code[tok];
+                uint32_t cw = S.code[tok_byte(tok)];
                 nbits = cw >> 16;
                 b = cw & 0xffffu;
             } else {
                 uint32_t ls, le, lv, ds, de, dv;
                 len_symbol(len, ls, le, lv);
-                dist_symbol(tok & 0xffffu, ds, de, dv);
+                dist_symbol(tok_dist(tok), ds, de, dv);
                 uint32_t cl = S.code[ls], cd = S.code[ZWZ_DE_DOFF + ds];
                 b = cl & 0xffffu;
                 nbits = cl >> 16;
@@ -558,7 +561,8 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         uint32_t m1 = __shfl_down_sync(ZWZ_FULL, m0, 1);
         const uint32_t mfirst = __shfl_sync(ZWZ_FULL, mnx, 0);
         if (lane == 31u) m1 = mfirst;
-        uint32_t len0 = m0 >> 16, len1 = m1 >> 16;
+        if (lane < 4u && p + 384u + 32u * lane < n) prefetch_l2(m + p + 384u + 32u * lane); // pull the scratch ahead of the parse into L2 (it sits in HBM)
+        uint32_t len0 = tok_len(m0), len1 = tok_len(m1);
         bool take = len0 >= ZWZ_MIN_MATCH && !(len1 > len0);
         uint32_t J = lane + (take ? len0 : 1u);
         uint32_t R = 1u << lane;
@@ -582,13 +586,13 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
                 tok = m0;
                 uint32_t ls, le, lv, ds, de, dv;
                 len_symbol(len0, ls, le, lv);
-                dist_symbol(m0 & 0xffffu ? (m0 & 0xffffu) : 65536u, ds, de, dv);
+                dist_symbol(tok_dist(m0), ds, de, dv);
                 atomicAdd(&S.freq[ls], 1u);
                 atomicAdd(&S.freq[ZWZ_DE_DOFF + ds], 1u);
                 extra_bits += le + de;
             } else {
-                tok = src[q];
-                atomicAdd(&S.freq[tok], 1u);
+                tok = m0 & 0xff000000u; // literal: the byte travels in the scratch word, no second load
+                atomicAdd(&S.freq[m0 >> 24], 1u);
             }
             m[ntok + (uint32_t) __popc(tm & ((1u << lane) - 1u))] = tok;
         }

@@ -17,8 +17,8 @@
 //   4. all warps pull 32-position tiles and, one lane per position, walk the chain:
 //      byte checks around the current best length reject most candidates, survivors are compared 4 bytes at a time on
 //      funnel-shifted aligned words; `depth` candidates at most, stop at `nice` bytes;
-//   5. the best (length, distance) of EVERY position goes to the chunk's scratch in HBM (4 bytes per input byte,
-//      coalesced); the parse in deflate_encode.cuh picks the path through them;
+//   5. the best (length, distance) of EVERY position, together with the byte at that position, goes to the chunk's scratch
+//      in HBM (4 bytes per input byte, coalesced); the parse in deflate_encode.cuh picks the path through them;
 //   6. Adler-32 of the chunk is reduced from shared memory while it is there.
 //
 // Four size classes so that small chunks do not leave an SM to one serial chain builder (config C2 is 370 000 chunks of
@@ -317,7 +317,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 }
                 if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             }
-            if (p < n) mout[p] = best_len >= 3u ? ((best_len << 16) | best_dist) : 0u;
+            if (p < n) mout[p] = tok_make(lds8(sD + p), best_len >= 3u ? best_len : 0u, best_dist);
             const unsigned hit = __ballot_sync(ZWZ_FULL, best_len >= 3u);
             if (lane == 0 && hit) atomicAdd(&ctl->nmatch, (uint32_t) __popc(hit));
         }

@@ -127,6 +127,18 @@ ZWZ_DEV uint32_t warp_max(uint32_t v) {
     return v;
 }
 
+// ---- scratch word per position / token: [31:24] literal byte at that position, [23:15] match length (0 = none, else 3..258),
+//      [14:0] match distance - 1. The parser keeps the words it selects (as tokens) and drops the others.
+ZWZ_DEV uint32_t tok_make(uint32_t byte, uint32_t len, uint32_t dist) { return (byte << 24) | (len << 15) | (len ? dist - 1u : 0u); }
+ZWZ_DEV uint32_t tok_len(uint32_t t) { return (t >> 15) & 0x1ffu; }
+ZWZ_DEV uint32_t tok_dist(uint32_t t) { return (t & 0x7fffu) + 1u; }
+ZWZ_DEV uint32_t tok_byte(uint32_t t) { return t >> 24; }
+#ifdef ZWZ_EMU
+ZWZ_DEV void prefetch_l2(const void *) {}
+#else
+ZWZ_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // ---- DEFLATE symbol arithmetic (RFC 1951 §3.2.5) without tables ----------------------------------------------------
 // length 3..258 -> (symbol 257..285, extra bit count, extra value)
 ZWZ_DEV void len_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
