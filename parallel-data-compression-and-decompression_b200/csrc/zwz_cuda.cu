@@ -80,7 +80,7 @@ struct zwz_ctx {
     std::string err;
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, counter;
-    size_t batch_raw_bytes = (size_t) 1 << 30; // raw bytes per internal deflate sub-batch (scratch = 4x that)
+    size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
     bool profiling = false;
