@@ -509,6 +509,25 @@ def main():
         cnt = torch.stack(allc).sum(0)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     U_all, C_all, n_all, nf_all, launches_all = [float(x) for x in cnt]
+    # ---- the chunk-offset exchange: when ONE file is cut into contiguous chunk ranges over the
+    # GPUs, all its records must land in ONE archive (decompression.cpp:52-55), so every rank needs the byte offset at which
+    # its records start: record bytes per rank -> all-gather -> exclusive scan. 13 + path_len header bytes per record, +32 for
+    # the MD5 behind the file's last record. Sequence ids are offset the same way (records, not chunks: split chunks count twice).
+    exchange = None
+    if args.workload == "c3":
+        path_len = len("big/huge.log")
+        n_records = int(n + int((res["len1"] > 0).sum()))
+        rec_bytes = Cbytes + n_records * (13 + path_len) + (32 if rank == world - 1 else 0)
+        mine = torch.tensor([float(rec_bytes), float(n_records)], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allv, mine)
+        else:
+            allv = [mine]
+        sizes_ = [int(v[0]) for v in allv]
+        recs_ = [int(v[1]) for v in allv]
+        exchange = {"rank_record_bytes": sizes_, "rank_write_offset": [int(sum(sizes_[:i])) for i in range(world)],
+                    "rank_first_sequence_id": [int(sum(recs_[:i])) for i in range(world)], "archive_bytes": int(sum(sizes_))}
 
     if rank == 0:
         K = args.steps
@@ -547,6 +566,7 @@ def main():
             "e2e": {"value": U_all * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(U + state["C"]),
                     "d2h_bytes_per_step": int(U + state["C"]), "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches_all),
+            "zwz_offset_exchange": exchange,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
