@@ -163,6 +163,11 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         const uint32_t nsteps = (nhash + 31u) >> 5;
         const uint32_t spw = (nsteps + NW - 1u) / NW;  // steps per warp: warp w owns positions [w*spw*32, (w+1)*spw*32)
 
+        const uint32_t sD = smem_addr(smem) + skew; // shared address of chunk byte 0
+        const uint32_t sP = smem_addr(prev);        // prev[0]
+        const uint32_t sH = smem_addr(head);        // head[0]
+        const uint32_t sC = smem_addr(cnt);         // cnt[0]
+        const uint32_t sB = smem_addr(&ctl->base[0]);
         // ---- 2. hash every position; count, per warp, how many of its positions fall in each of the NW hash ranges ----
         // Same-range lanes of a step are found with LB ballots (a 5-bit match_any), so ranks inside a step follow lane
         // (= position) order and the lists come out sorted by position.
@@ -171,9 +176,9 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             const bool valid = p < nhash;
             uint32_t h = 0;
             if (valid) {
-                uint32_t v = ld32u(dataw, skew + p);
+                uint32_t v = lds32u(sD + p);
                 h = dm_hash3<HB>(v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu);
-                prev[p] = (uint16_t) h; // prev[p] holds hash(p) until the builder replaces it by the link
+                sts16(sP + 2u * p, h); // prev[p] holds hash(p) until the builder replaces it by the link
             }
             const uint32_t b = h >> (HB - LB);
             unsigned m = __ballot_sync(ZWZ_FULL, valid);
@@ -182,7 +187,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 unsigned v = __ballot_sync(ZWZ_FULL, (b >> k) & 1u);
                 m &= ((b >> k) & 1u) ? v : ~v;
             }
-            if (valid && (m >> lane) == 1u) cnt[wid * NW + b] += (uint16_t) __popc(m); // entry owned by this warp
+            if (valid && (m >> lane) == 1u) sts16(sC + 2u * (wid * NW + b), lds16(sC + 2u * (wid * NW + b)) + (uint32_t) __popc(m)); // entry owned by this warp
             __syncwarp();
         }
         __syncthreads();
@@ -205,7 +210,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         for (uint32_t st = wid * spw; st < (wid + 1u) * spw && st < nsteps; ++st) {
             const uint32_t p = st * 32u + lane;
             const bool valid = p < nhash;
-            const uint32_t h = valid ? (uint32_t) prev[p] : 0u;
+            const uint32_t h = valid ? lds16(sP + 2u * p) : 0u;
             const uint32_t b = h >> (HB - LB);
             unsigned m = __ballot_sync(ZWZ_FULL, valid);
 #pragma unroll
@@ -214,11 +219,11 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 m &= ((b >> k) & 1u) ? v : ~v;
             }
             if (valid) {
-                uint32_t slot = ctl->base[b] + cnt[wid * NW + b] + (uint32_t) __popc(m & lt);
+                uint32_t slot = lds32(sB + 4u * b) + lds16(sC + 2u * (wid * NW + b)) + (uint32_t) __popc(m & lt);
                 list[slot] = (uint16_t) p;
             }
             __syncwarp();
-            if (valid && (m >> lane) == 1u) cnt[wid * NW + b] += (uint16_t) __popc(m);
+            if (valid && (m >> lane) == 1u) sts16(sC + 2u * (wid * NW + b), lds16(sC + 2u * (wid * NW + b)) + (uint32_t) __popc(m));
             __syncwarp();
         }
         __threadfence_block();
@@ -238,16 +243,16 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 const bool valid = i0 + lane < i_end;
                 const uint32_t q = qn;
                 qn = (i0 + 32u + lane < i_end) ? (uint32_t) __ldcg(list + i0 + 32u + lane) : 0u; // next step, fetched ahead
-                const uint32_t h = valid ? (uint32_t) prev[q] : 0u;
+                const uint32_t h = valid ? lds16(sP + 2u * q) : 0u;
                 uint32_t old = ZWZ_DM_NIL;
-                if (valid) old = head[h];
+                if (valid) old = lds16(sH + 2u * h);
                 __syncwarp(); // all reads of head[] precede the writes of this step
                 if (valid) {
-                    prev[q] = (uint16_t) old;
-                    head[h] = (uint16_t) q;
+                    sts16(sP + 2u * q, old);
+                    sts16(sH + 2u * h, q);
                 }
                 __syncwarp();
-                uint32_t rb = valid ? (uint32_t) head[h] : q;
+                uint32_t rb = valid ? lds16(sH + 2u * h) : q;
                 unsigned rem = __ballot_sync(ZWZ_FULL, rb != q); // lanes that lost a store race
                 while (rem) {                                    // one round per colliding group (warp-uniform loop)
                     const int leader = __ffs((int) rem) - 1;
@@ -258,8 +263,8 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                     const int from = (mine && lower) ? 31 - __clz((int) lower) : (int) lane;
                     const uint32_t qlow = __shfl_sync(ZWZ_FULL, q, from);  // nearest earlier position of the group
                     if (mine) {
-                        if (lower) prev[q] = (uint16_t) qlow;
-                        if ((same >> lane) == 1u) head[h] = (uint16_t) q;    // the latest position stays head
+                        if (lower) sts16(sP + 2u * q, qlow);
+                        if ((same >> lane) == 1u) sts16(sH + 2u * h, q);        // the latest position stays head
                     }
                     rem &= ~same;
                 }
@@ -269,8 +274,6 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         // ---- 6. search: one lane per position, 32-position tiles ----
-        const uint32_t sD = smem_addr(smem) + skew; // shared address of chunk byte 0
-        const uint32_t sP = smem_addr(prev);        // shared address of prev[0]
         for (;;) {
             uint32_t tile = 0;
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);

@@ -169,6 +169,7 @@ struct InfBits {
     uint32_t skew;          // byte offset of the stream inside that word
     uint32_t nbytes;        // stream length
     uint32_t nwords;        // words covering [skew, skew + nbytes)
+    uint32_t nfull;         // leading words that lie entirely inside the stream: while widx <= nfull every fed bit is real
     uint32_t widx;          // next word to feed
     uint32_t cache, cache_next;
     uint32_t cache_blk;     // block (32 words) held in `cache`; cache_next holds cache_blk + 1
@@ -241,6 +242,7 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
     B.wbase = (const uint32_t *) (comp - B.skew);
     B.nbytes = comp_len;
     B.nwords = (B.skew + comp_len + 3u) >> 2;
+    B.nfull = (B.skew + comp_len) >> 2;
     infb_seek(B, 0);
 
     uint32_t pos = 0;       // bytes produced (counted past cap too)
@@ -257,7 +259,8 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
     } while (0)
 // Everything already in `hold` is real stream data while fed <= total_bits; only the tail of a stream (or a truncated
 // one) needs the per-symbol availability checks that give zlib's exact stop position.
-#define INF_NEED(nbits_) (B.fed <= total_bits || infb_used(B) + (uint64_t) (nbits_) <= total_bits)
+#define INF_FAST() (B.widx <= B.nfull)
+#define INF_NEED(nbits_) (INF_FAST() || infb_used(B) + (uint64_t) (nbits_) <= total_bits)
 
     // ---- RFC 1950 header (inflate.c HEAD) ----
     infb_refill(B);
@@ -325,6 +328,7 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
         }
 
         uint32_t max_ll = 0, max_d = 0;
+        uint32_t min_ll = 1; // shortest literal/length code of this block: bounds how many codes fit a 32-bit window
         if (type == 1u) {
             for (uint32_t s = lane; s < 288u; s += 32u) S.lens[32u + s] = (uint8_t) (s < 144u ? 8 : (s < 256u ? 9 : (s < 280u ? 7 : 8)));
             S.lens[320u + lane] = 5;
@@ -427,11 +431,12 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
             }
         }
 
+        for (min_ll = 1; min_ll < 15u && S.cnt_ll[min_ll] == 0u; ++min_ll) {}
         // ---- symbol loop ----
         for (;;) {
             infb_refill(B); // >= 33 valid bits
             uint32_t e;
-            if (B.fed <= total_bits) {
+            if (INF_FAST()) {
                 // Literal runs, 32 bit offsets at a time ("warp-ballot symbol decode"): lane l decodes the code that WOULD
                 // start at bit l of the buffer; the ballot says which offsets hold a complete literal; the offsets that
                 // really are code starts form the chain 0 -> nb(0) -> ..., recovered with 5 rounds of pointer doubling on
@@ -444,8 +449,9 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
                 if (litmask & 1u) {
                     uint32_t J = lane + (el & 15u);
                     uint32_t R = ok ? (1u << lane) : 0u;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) {
+                    // a window of 32 bits holds at most 32 / min_ll code starts: 3 doubling rounds reach 8 of them, 4 reach 16
+                    const int rounds = min_ll >= 4u ? 3 : (min_ll >= 2u ? 4 : 5);
+                    for (int r = 0; r < rounds; ++r) {
                         const bool go = ok && J < 32u && ((litmask >> J) & 1u);
                         const int from = go ? (int) J : (int) lane;
                         const uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);

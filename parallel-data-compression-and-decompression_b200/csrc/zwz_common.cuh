@@ -69,29 +69,32 @@ ZWZ_DEV uint32_t ld32u(const uint32_t *w, uint32_t i) {
 // ---- explicit shared-memory addressing for the hot loops --------------------------------------------------------------
 // A 32-bit shared-window address + ld.shared keeps the inner loops at one LDS per access; going through generic pointers made
 // the compiler rebuild the window base (S2R SR_CgaCtaId / LEA) inside the candidate loop. Emulator: offset into the CTA's
-// dynamic shared memory.
+// dynamic shared memory. The asm statements are volatile with a memory clobber: they must not move across barriers or the
+// stores of the chain builder.
 #ifdef ZWZ_EMU
 ZWZ_DEV uint32_t smem_addr(const void *p) { return (uint32_t) ((const unsigned char *) p - simt::dyn_smem()); }
 ZWZ_DEV uint32_t lds8(uint32_t a) { return simt::dyn_smem()[a]; }
 ZWZ_DEV uint32_t lds16(uint32_t a) { return *(const uint16_t *) (simt::dyn_smem() + a); }
 ZWZ_DEV uint32_t lds32(uint32_t a) { return *(const uint32_t *) (simt::dyn_smem() + a); }
+ZWZ_DEV void sts16(uint32_t a, uint32_t v) { *(uint16_t *) (simt::dyn_smem() + a) = (uint16_t) v; }
 #else
 ZWZ_DEV uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 ZWZ_DEV uint32_t lds8(uint32_t a) {
     uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 ZWZ_DEV uint32_t lds16(uint32_t a) {
     uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 ZWZ_DEV uint32_t lds32(uint32_t a) {
     uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+ZWZ_DEV void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short) v) : "memory"); }
 #endif
 // unaligned little-endian 32-bit load at shared address a
 ZWZ_DEV uint32_t lds32u(uint32_t a) {
