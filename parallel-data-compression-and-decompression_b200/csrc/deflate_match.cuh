@@ -26,7 +26,7 @@
 // holds.
 //      class   chunk bytes   threads   smem/CTA   CTAs/SM   hash bits
 //        0       <=  8 192      256     ~33 KB       6         12
-//        1       <= 16 384      512     ~58 KB       3         12
+//        1       <= 16 384      512     ~66 KB       3         13
 //        2       <= 32 768      512    ~114 KB       2         13
 //        3       <= 65 535     1024    ~227 KB       1         14
 // Algorithmic HBM bytes per chunk for the roofline: N_raw read (the 4 N_raw scratch write is traffic of this design, not of
@@ -44,7 +44,7 @@ template <> struct MatchClass<0> {
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 8u * 8u;
 };
 template <> struct MatchClass<1> {
-    static constexpr uint32_t kCap = 16384, kThreads = 512, kHBits = 12, kData = 16384 + 64, kListBits = 4;
+    static constexpr uint32_t kCap = 16384, kThreads = 512, kHBits = 13, kData = 16384 + 64, kListBits = 4;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<2> {

@@ -197,4 +197,140 @@ ZWZ_KERNEL md5_files_kernel(const uint8_t *__restrict__ data, const uint64_t *__
     }
 }
 
+// ---- large files: same one-lane-per-file chain, but the bytes arrive through shared memory -----------------------------
+// With few, long files the per-lane loads above are the problem: 32 lanes x 16 scattered words per block, every block a
+// fresh trip to HBM in front of 64 dependent steps. Here a warp copies, for each of its 32 files in turn, the next 512 bytes
+// with cp.async (32 lanes x 4 B = one coalesced 128-byte line per instruction) into a per-lane row of a double-buffered
+// staging area while all lanes hash the previous 512 bytes of their own rows. Row stride = 129 words: lane l reads word k
+// of its row from bank (l + k) mod 32 — conflict-free.
+#define ZWZ_MD5S_WARPS 2
+#define ZWZ_MD5S_ROUND 512u                     // bytes per file per round (8 MD5 blocks)
+#define ZWZ_MD5S_ROW 129u                       // words per row (128 + 1 pad)
+#define ZWZ_MD5S_SMEM (ZWZ_MD5S_WARPS * 2u * 32u * (ZWZ_MD5S_ROW + 3u) * 4u)
+
+#ifdef ZWZ_EMU
+ZWZ_DEV void md5s_cp4(uint32_t *dst, const uint32_t *src) { *dst = *src; }
+ZWZ_DEV void md5s_commit() {}
+ZWZ_DEV void md5s_wait_all() {}
+#else
+ZWZ_DEV void md5s_cp4(uint32_t *dst, const uint32_t *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+ZWZ_DEV void md5s_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ZWZ_DEV void md5s_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
+// Each row holds the aligned words covering bytes [round*512, round*512 + 512 + 3] of the file's aligned stream (one extra
+// word so the funnel shift of an unaligned file has its right neighbour): 129 data words + pad.
+ZWZ_KERNEL __launch_bounds__(ZWZ_MD5S_WARPS * 32) md5_files_staged_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off,
+                                                                         const uint64_t *__restrict__ len,
+                                                                         const uint64_t *__restrict__ total_len, uint32_t *state,
+                                                                         uint8_t *digest, uint32_t n, int finalize) {
+    ZWZ_DYN_SMEM(smem);
+    const unsigned lane = lane_id(), wid = warp_id();
+    constexpr uint32_t ROWW = ZWZ_MD5S_ROW + 3u; // 132 words: 129 used, keeps rows 16-byte aligned
+    uint32_t *stage = (uint32_t *) smem + (size_t) wid * 2u * 32u * ROWW;
+    const uint32_t i = (blockIdx.x * ZWZ_MD5S_WARPS + wid) * 32u + lane;
+    const bool have = i < n;
+    uint32_t st[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    if (have && state) {
+        st[0] = state[4 * i + 0];
+        st[1] = state[4 * i + 1];
+        st[2] = state[4 * i + 2];
+        st[3] = state[4 * i + 3];
+    }
+    const uint8_t *p = have ? data + off[i] : data;
+    const uint64_t L = have ? len[i] : 0;
+    const uint64_t nblk = L >> 6;
+    const uint32_t skew = (uint32_t) ((uintptr_t) p & 3u);
+    const uint32_t *w = (const uint32_t *) (p - skew);
+    // words of the aligned stream that may be read: covers every full block (+1 neighbour word when skewed)
+    const uint64_t nwords = nblk * 16u + (skew && nblk ? 1u : 0u);
+    const uint64_t rounds = (nblk + 7u) >> 3;
+    uint64_t max_rounds = rounds;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uint64_t o = __shfl_xor_sync(ZWZ_FULL, max_rounds, d);
+        max_rounds = o > max_rounds ? o : max_rounds;
+    }
+    // cooperative fill of buffer `buf` with round r of all 32 files
+    auto fill = [&](uint32_t buf, uint64_t r) {
+        for (uint32_t f = 0; f < 32u; ++f) {
+            const uint32_t *fw = (const uint32_t *) __shfl_sync(ZWZ_FULL, (unsigned long long) w, (int) f);
+            const uint64_t fnw = __shfl_sync(ZWZ_FULL, (unsigned long long) nwords, (int) f);
+            const uint64_t base = r * 128u;
+            if (base >= fnw) continue; // warp-uniform
+            uint32_t *row = stage + ((size_t) buf * 32u + f) * ROWW;
+#pragma unroll
+            for (uint32_t c = 0; c < 4u; ++c) {
+                uint64_t k = base + c * 32u + lane;
+                if (k < fnw) md5s_cp4(row + c * 32u + lane, fw + k);
+            }
+            if (lane == 0 && base + 128u < fnw) md5s_cp4(row + 128u, fw + base + 128u); // right neighbour for the funnel shift
+        }
+        md5s_commit();
+    };
+    if (max_rounds) fill(0, 0);
+    for (uint64_t r = 0; r < max_rounds; ++r) {
+        md5s_wait_all();
+        __syncwarp();
+        if (r + 1 < max_rounds) fill((uint32_t) ((r + 1) & 1u), r + 1);
+        if (r < rounds) {
+            const uint32_t *row = stage + ((size_t) (r & 1u) * 32u + lane) * ROWW;
+            const uint64_t b0 = r * 8u;
+            const uint32_t nb = (uint32_t) (nblk - b0 < 8u ? nblk - b0 : 8u);
+            const uint32_t sh = skew * 8u;
+            for (uint32_t b = 0; b < nb; ++b) {
+                uint32_t m[16];
+                if (skew == 0) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) m[k] = row[b * 16u + k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) m[k] = __funnelshift_r(row[b * 16u + k], row[b * 16u + k + 1], sh);
+                }
+                md5_block(st, m);
+            }
+        }
+        __syncwarp();
+    }
+    if (!have) return;
+    if (finalize) {
+        const uint8_t *t = p + (nblk << 6);
+        uint32_t r = (uint32_t) (L & 63u);
+        uint64_t bits = (total_len ? total_len[i] : L) * 8ull;
+        uint32_t m[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t idx = 4u * k + j;
+                uint32_t byte = idx < r ? (uint32_t) t[idx] : (idx == r ? 0x80u : 0u);
+                v |= byte << (8 * j);
+            }
+            m[k] = v;
+        }
+        if (r >= 56u) {
+            md5_block(st, m);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[k] = 0;
+        }
+        m[14] = (uint32_t) bits;
+        m[15] = (uint32_t) (bits >> 32);
+        md5_block(st, m);
+        uint32_t *dg = (uint32_t *) (digest + 16ull * i);
+        dg[0] = st[0];
+        dg[1] = st[1];
+        dg[2] = st[2];
+        dg[3] = st[3];
+    }
+    if (state) {
+        state[4 * i + 0] = st[0];
+        state[4 * i + 1] = st[1];
+        state[4 * i + 2] = st[2];
+        state[4 * i + 3] = st[3];
+    }
+}
+
 } // namespace zwz

@@ -203,7 +203,8 @@ int zwz_init(int device, zwz_ctx **out) {
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<0>, zwz::MatchClass<0>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<1>, zwz::MatchClass<1>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem) ||
-        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<3>, zwz::MatchClass<3>::kSmem)) {
+        zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<3>, zwz::MatchClass<3>::kSmem) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::md5_files_staged_kernel, ZWZ_MD5S_SMEM)) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
@@ -759,10 +760,21 @@ static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, cons
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint8_t *d_digest = dm + r_base;
     {
+        // few long files: the staged kernel (coalesced cp.async into shared memory); many short ones: one lane streams its file
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) total += len[i];
+        const bool staged = total / n >= 65536u;
         ProfSpan ps(ctx, ZWZ_PROF_MD5, st);
-        ZWZ_LAUNCH(zwz::md5_files_kernel, (n + 127) / 128, 128, 0, st, d_data, (const uint64_t *) dm, (const uint64_t *) (dm + m_len),
-                   total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr,
-                   state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr, d_digest, n, finalize);
+        if (staged) {
+            const uint32_t per_cta = ZWZ_MD5S_WARPS * 32u;
+            ZWZ_LAUNCH(zwz::md5_files_staged_kernel, (n + per_cta - 1) / per_cta, per_cta, ZWZ_MD5S_SMEM, st, d_data, (const uint64_t *) dm,
+                       (const uint64_t *) (dm + m_len), total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr,
+                       state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr, d_digest, n, finalize);
+        } else {
+            ZWZ_LAUNCH(zwz::md5_files_kernel, (n + 127) / 128, 128, 0, st, d_data, (const uint64_t *) dm, (const uint64_t *) (dm + m_len),
+                       total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr,
+                       state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr, d_digest, n, finalize);
+        }
     }
     if ((rc = check_launch(ctx, "md5_files_kernel"))) return rc;
     if (finalize && zwz_rt::memcpy_d2h(hp, d_digest, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "digest download failed");

@@ -48,21 +48,45 @@ struct FileState {
     bool complete = false;       // the ordered run ends with an is_last record
 };
 
-bool read_whole(const std::string &path, std::vector<uint8_t> &buf) {
+// grow-only page-locked host buffer (uploads/downloads straight from/to it run at full PCIe speed, and growing it does
+// not zero-fill gigabytes the way std::vector::resize does)
+struct PinnedBuf {
+    zwz_ctx *ctx = nullptr;
+    uint8_t *p = nullptr;
+    size_t cap = 0, len = 0;
+    explicit PinnedBuf(zwz_ctx *c) : ctx(c) {}
+    ~PinnedBuf() {
+        if (p) zwz_free_pinned(ctx, p);
+    }
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) zwz_free_pinned(ctx, p);
+        p = nullptr;
+        cap = n + n / 8 + 4096;
+        if (zwz_malloc_pinned(ctx, cap, (void **) &p) != ZWZ_OK) throw std::runtime_error("zwz: pinned allocation failed");
+    }
+    uint8_t *data() { return p; }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return len; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+};
+
+bool read_whole(const std::string &path, PinnedBuf &buf) {
     std::FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
     std::fseek(f, 0, SEEK_END);
     long n = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
-    buf.resize(n > 0 ? (size_t) n : 0);
-    size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
+    buf.reserve(n > 0 ? (size_t) n : 1);
+    buf.len = n > 0 ? std::fread(buf.data(), 1, (size_t) n, f) : 0;
     std::fclose(f);
-    buf.resize(got);
     return true;
 }
 
 // decompression.cpp:65-92
-void parse_archive(const std::vector<uint8_t> &a, std::vector<FileState> &files) {
+void parse_archive(const PinnedBuf &a, std::vector<FileState> &files) {
     std::map<std::string, size_t> index;
     std::map<std::string, int> expected;                 // the reference's expected_sequence_id, simulated
     std::map<std::string, std::vector<int>> pending;     // seqs sitting in the heap
@@ -70,13 +94,13 @@ void parse_archive(const std::vector<uint8_t> &a, std::vector<FileState> &files)
     const size_t n = a.size();
     while (o + 4 <= n) {
         int total_size, path_length;
-        std::memcpy(&total_size, &a[o], 4);
+        std::memcpy(&total_size, a.data() + o, 4);
         if (o + 8 > n) break;
-        std::memcpy(&path_length, &a[o + 4], 4);
+        std::memcpy(&path_length, a.data() + o + 4, 4);
         if (path_length < 0 || o + 8 + (size_t) path_length + 5 > n) break;
-        std::string relpath((const char *) &a[o + 8], (size_t) path_length);
+        std::string relpath((const char *) a.data() + o + 8, (size_t) path_length);
         int sequence_id;
-        std::memcpy(&sequence_id, &a[o + 8 + path_length], 4);
+        std::memcpy(&sequence_id, a.data() + o + 8 + path_length, 4);
         bool is_last = a[o + 12 + path_length] != 0;
         long payload = (long) total_size - (4 + path_length + 4 + 1);
         size_t p0 = o + 13 + (size_t) path_length;
@@ -85,10 +109,10 @@ void parse_archive(const std::vector<uint8_t> &a, std::vector<FileState> &files)
         std::string md5;
         if (is_last) {
             if (o + MD5_DATA_SIZE > n) {
-                md5.assign((const char *) &a[o], n - o);
+                md5.assign((const char *) a.data() + o, n - o);
                 o = n;
             } else {
-                md5.assign((const char *) &a[o], MD5_DATA_SIZE);
+                md5.assign((const char *) a.data() + o, MD5_DATA_SIZE);
                 o += MD5_DATA_SIZE;
             }
         }
@@ -157,8 +181,7 @@ void print_verdict(const std::string &file_path, const std::string &stored, cons
 
 // A file whose records do not fit one batch: sub-batches of consecutive records are appended to the output file and the
 // MD5 is taken the way the reference takes it — by reading the finished file back (decompression.cpp:136).
-void big_file(zwz_ctx *ctx, const std::vector<uint8_t> &arch, FileState &fsx, const std::string &output_dir, uint64_t budget,
-              std::vector<uint8_t> &out) {
+void big_file(zwz_ctx *ctx, const PinnedBuf &arch, FileState &fsx, const std::string &output_dir, uint64_t budget, PinnedBuf &out) {
     const RunConfig &cfg = config();
     std::string file_path = output_dir + "/" + fsx.relpath;
     ensure_parent(file_path);
@@ -180,9 +203,9 @@ void big_file(zwz_ctx *ctx, const std::vector<uint8_t> &arch, FileState &fsx, co
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
-            if (out.size() < need + 64) out.resize(need + 64);
+            out.reserve(need + 64);
             int rc = zwz_decompress_records(ctx, arch.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, 1, out.data(),
-                                            out.size(), foff.data(), raw_len.data(), status.data(), nullptr, 0);
+                                            out.cap, foff.data(), raw_len.data(), status.data(), nullptr, 0);
             if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx));
             bool again = false;
             for (size_t i = 0; i < nrec; ++i)
@@ -205,7 +228,8 @@ void big_file(zwz_ctx *ctx, const std::vector<uint8_t> &arch, FileState &fsx, co
 
 void decompress_zwz(const std::string &filename, const std::string &output_dir) {
     const RunConfig &cfg = config();
-    std::vector<uint8_t> arch;
+    zwz_ctx *ctx = ctx_for(cfg.device);
+    PinnedBuf arch(ctx);
     double t0 = now_seconds();
     if (!read_whole(filename, arch)) {
         std::cerr << "Error opening file: " << filename << std::endl;
@@ -214,11 +238,10 @@ void decompress_zwz(const std::string &filename, const std::string &output_dir) 
     std::vector<FileState> files;
     parse_archive(arch, files);
     stats().t_read += now_seconds() - t0;
-    zwz_ctx *ctx = ctx_for(cfg.device);
 
     // groups of whole files, bounded by the raw bytes they may produce
     const uint64_t budget = std::max<uint64_t>(cfg.batch_bytes, 4 * CHUNK_SIZE);
-    std::vector<uint8_t> out;
+    PinnedBuf out(ctx);
     size_t fi = 0;
     while (fi < files.size()) {
         if (files[fi].ordered.size() * CHUNK_SIZE > budget) { // one file larger than a batch: stream its records through
@@ -250,9 +273,9 @@ void decompress_zwz(const std::string &filename, const std::string &output_dir) 
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
-            if (out.size() < need + 64) out.resize(need + 64);
+            out.reserve(need + 64);
             int rc = zwz_decompress_records(ctx, arch.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf, out.data(),
-                                            out.size(), foff.data(), raw_len.data(), status.data(), digest.data(), 0);
+                                            out.cap, foff.data(), raw_len.data(), status.data(), digest.data(), 0);
             if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx));
             bool again = false;
             for (size_t i = 0; i < nrec; ++i)

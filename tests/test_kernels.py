@@ -45,6 +45,22 @@ def test_md5_rfc_and_padding(ctx):
             assert bytes(d).hex() == O.md5_hex(f) == hashlib.md5(f).hexdigest()
 
 
+def test_md5_large_files_staged_path(ctx, is_gpu):
+    """Files averaging >= 64 KiB take the shared-memory staged kernel (coalesced cp.async); every alignment, ragged lengths."""
+    rng = np.random.Generator(np.random.Philox(key=[596, 8]))
+    nfiles = 70 if is_gpu else 37   # more than one warp, last warp partial
+    sizes = rng.integers(66_000, 400_000 if is_gpu else 140_000, size=nfiles)
+    sizes[3] = 65536 * 2
+    sizes[5] = 64 * 1031 + 63
+    files = [corpus.gen_random(int(n), 596, 900 + i).tobytes() for i, n in enumerate(sizes)]
+    buf, off = _cat(files)
+    for shift in (0, 1, 3):
+        data = b"\x00" * shift + buf
+        dg = ctx.md5_batch(data, off[:-1] + np.uint64(shift), np.diff(off))
+        for f, d in zip(files, dg):
+            assert bytes(d).hex() == hashlib.md5(f).hexdigest()
+
+
 def test_md5_streaming_update_final(ctx):
     raw = corpus.gen_text(300_000, 596, 9)
     d = ctx.malloc_device(raw.nbytes + 64)
