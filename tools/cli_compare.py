@@ -119,6 +119,28 @@ def main():
         x2 = os.path.join(tmp, "x2")
         _, outs = run_ranks(MAIN, ["decompress", ref_arch, x2], 1, lambda r: {})
         ok2, _ = same_tree(ref_out, x2)
+        if not ok2:  # diagnostics: which files differ, where
+            diffs = []
+            for d, _, fs in os.walk(ref_out):
+                for f in fs:
+                    pa = os.path.join(d, f)
+                    pb = os.path.join(x2, os.path.relpath(pa, ref_out))
+                    if not os.path.exists(pb):
+                        diffs.append({"file": os.path.relpath(pa, ref_out), "missing": True})
+                        continue
+                    a_, b_ = open(pa, "rb").read(), open(pb, "rb").read()
+                    if a_ != b_:
+                        k = next((i for i in range(min(len(a_), len(b_))) if a_[i] != b_[i]), min(len(a_), len(b_)))
+                        diffs.append({"file": os.path.relpath(pa, ref_out), "ref_size": len(a_), "our_size": len(b_), "first_diff": k,
+                                      "src_size": os.path.getsize(os.path.join(src, os.path.relpath(pa, ref_out)))})
+            res["we_read_refs_diffs"] = diffs[:40]
+            keep = os.path.join(ROOT, "gpurun_out", "diff_case")
+            shutil.rmtree(keep, ignore_errors=True)
+            os.makedirs(keep, exist_ok=True)
+            if diffs and "ref_size" in diffs[0] and diffs[0]["src_size"] < 6_000_000:   # keep the smallest differing source file for a local repro
+                small = min((d_ for d_ in diffs if "src_size" in d_), key=lambda d_: d_["src_size"])
+                shutil.copy(os.path.join(src, small["file"]), os.path.join(keep, "source.bin"))
+                res["kept_case"] = small
         res["we_read_refs"] = {"identical_to_ref_output": ok2, "md5_match": outs[0].count("MD5 match for file"),
                                "md5_mismatch": outs[0].count("MD5 mismatch for file")}
         res["size_vs_ref"] = res["our_archive_bytes"] / res["ref_archive_bytes"]
