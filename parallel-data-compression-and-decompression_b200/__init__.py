@@ -80,6 +80,7 @@ def _declare(L):
     L.zwz_md5_hex.argtypes = [vp, vp]
     L.zwz_md5_hex.restype = None
     L.zwz_adler32_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp]
+    L.zwz_decompress_records.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, vp, u64, vp, vp, vp, vp, u32]
     L.zwz_profile_enable.argtypes = [vp, i32]
     L.zwz_profile_read.argtypes = [vp, vp, vp, i32]
     return L
@@ -266,6 +267,24 @@ class Context:
         self._check(self.lib.zwz_inflate_batch_device(self.h, d_comp, _ptr(off), _ptr(length), n, d_raw_out, _ptr(raw_off), _ptr(rl), _ptr(st),
                                                       flags, stream or None))
         return rl, st
+
+    def decompress_records(self, comp, off, length, rec_cap, rec_file, nf: int, out_cap: int, want_md5: bool = True, flags: int = 0):
+        """Worker side of decompression.cpp:100-151 for a group of records (host buffers): inflate every record, concatenate the
+        records of each file in order, MD5 every file. Returns (files, file_off[nf+1], raw_len[n], status[n], digest[nf,16])."""
+        comp = _u8(comp)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        rec_cap = np.ascontiguousarray(rec_cap, dtype=np.uint32)
+        rec_file = np.ascontiguousarray(rec_file, dtype=np.uint32)
+        n = len(off)
+        files = np.zeros(max(out_cap, 1), dtype=np.uint8)
+        foff = np.zeros(nf + 1, dtype=np.uint64)
+        rl = np.zeros(n, dtype=np.uint32)
+        st = np.zeros(n, dtype=np.uint32)
+        dg = np.zeros((nf, 16), dtype=np.uint8)
+        self._check(self.lib.zwz_decompress_records(self.h, _ptr(comp), _ptr(off), _ptr(length), _ptr(rec_cap), _ptr(rec_file), n, nf, _ptr(files),
+                                                    out_cap, _ptr(foff), _ptr(rl), _ptr(st), _ptr(dg) if want_md5 else None, flags))
+        return files, foff, rl, st, dg
 
     # ---- MD5: verification.cpp:13-27 ----
     def md5_batch(self, data, off, length) -> np.ndarray:

@@ -79,7 +79,7 @@ struct zwz_ctx {
     zwz_stream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
-    zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, counter;
+    zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
@@ -226,6 +226,7 @@ void zwz_destroy(zwz_ctx *ctx) {
     release(ctx->bulk_out);
     release(ctx->packed);
     release(ctx->pin_meta);
+    release(ctx->pin_aux);
     release(ctx->counter);
     zwz_rt::stream_destroy(ctx->stream);
     delete ctx;
@@ -709,8 +710,10 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     if (acc > out_cap) return fail(ctx, ZWZ_E_CAPACITY, "output buffer too small");
     const size_t m_dst = (size_t) n * 8, m_len = 2 * (size_t) n * 8, meta_bytes = m_len + (size_t) n * 4;
     if ((rc = reserve(ctx, ctx->packed, (size_t) acc + align_up(meta_bytes, 256) + 256, false))) return rc;
-    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
-    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    // NOT pin_meta: md5_launch below refills pin_meta while this upload may still be in flight (page-locked memory is read by
+    // the DMA engine after cudaMemcpyAsync returns) — a reuse race that corrupted gather descriptors once per ~10^5 records.
+    if ((rc = reserve(ctx, ctx->pin_aux, meta_bytes, true))) return rc;
+    uint8_t *hp = (uint8_t *) ctx->pin_aux.p;
     memcpy(hp, slot.data(), (size_t) n * 8);
     memcpy(hp + m_dst, dst.data(), (size_t) n * 8);
     memcpy(hp + m_len, raw_len, (size_t) n * 4);

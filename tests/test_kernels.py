@@ -188,6 +188,38 @@ def test_inflate_golden_reference_archives(ctx, name, is_gpu):
         assert (len(data), hashlib.md5(data).hexdigest()) == (want["size"], want["md5"]), path
 
 
+def test_decompress_records_group_stress(ctx, is_gpu):
+    """decompression.cpp:100-151 for one group: inflate + in-order concatenation per file + MD5, many records over many files,
+    several times over. Repeats because the failure this pins was a race (the gather descriptors sat in a page-locked buffer
+    that the following MD5 launch refilled while the upload was still in flight): record 1 of the first file then landed on
+    another file's offset, about once per 10^5 records at 2 GB scale."""
+    rng = np.random.default_rng(596)
+    nf = 3000 if is_gpu else 40
+    reps = 6 if is_gpu else 1
+    nrec = rng.integers(1, 5, nf)
+    raws, comps, rec_file = [], [], []
+    for f in range(nf):
+        for k in range(int(nrec[f])):
+            ln = 65535 if k + 1 < nrec[f] else int(rng.integers(0, 9000))
+            if not is_gpu:
+                ln = min(ln, 3000)
+            raw = corpus.gen_file("TSJB"[f & 3], ln, 596, 7000 + f * 8 + k).tobytes()
+            raws.append(raw)
+            comps.append(zlib.compress(raw, 6))
+            rec_file.append(f)
+    comp, off = _cat(comps)
+    caps = np.full(len(comps), 65535, dtype=np.uint32)
+    total = sum(len(r) for r in raws)
+    want = b"".join(raws)
+    for _ in range(reps):
+        files, foff, rl, st, dg = ctx.decompress_records(comp, off[:-1], np.diff(off).astype(np.uint32), caps, rec_file, nf, total + 64)
+        assert (st == O.STREAM_END).all() and int(foff[nf]) == total
+        assert [int(x) for x in rl] == [len(r) for r in raws]
+        assert files[:total].tobytes() == want
+        for f in (0, 1, nf // 2, nf - 1):
+            assert dg[f].tobytes() == hashlib.md5(want[int(foff[f]):int(foff[f + 1])]).digest()
+
+
 # ------------------------------------------------------------------------------------------------------------ deflate
 def _deflate_and_verify(ctx, chunks, level=0):
     raw, off = _cat(chunks)
