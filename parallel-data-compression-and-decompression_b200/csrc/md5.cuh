@@ -15,10 +15,21 @@ namespace zwz {
 #define ZWZ_MD5_G(b, c, d) ((c) ^ ((d) & ((b) ^ (c))))
 #define ZWZ_MD5_H(b, c, d) ((b) ^ (c) ^ (d))
 #define ZWZ_MD5_I(b, c, d) ((c) ^ ((b) | ~(d)))
-#define ZWZ_MD5_STEP(f, a, b, c, d, m, k, s)            \
-    do {                                                \
-        (a) += f((b), (c), (d)) + (m) + (uint32_t) (k); \
-        (a) = __funnelshift_l((a), (a), (s)) + (b);     \
+// The chain through the freshest word (b) is LOP3 -> add -> LEA.HI (rotate + add): a + m + k does not depend on b and is
+// formed first, behind an optimisation barrier. (Left alone the compiler emits IADD3(f, a, m) followed by a separate add
+// of k: four dependent ops per step instead of three. ptxas still places the two-input add on the FMA pipe as IMAD.IADD;
+// attempts to force an ALU-pipe IADD3 there were re-associated away.)
+#ifdef ZWZ_EMU
+#define ZWZ_MD5_PIN(x) ((void) 0)
+#else
+#define ZWZ_MD5_PIN(x) asm("" : "+r"(x))
+#endif
+#define ZWZ_MD5_STEP(f, a, b, c, d, m, k, s)         \
+    do {                                             \
+        uint32_t t_ = (a) + (m) + (uint32_t) (k);    \
+        ZWZ_MD5_PIN(t_);                             \
+        t_ += f((b), (c), (d));                      \
+        (a) = __funnelshift_l(t_, t_, (s)) + (b);    \
     } while (0)
 
 ZWZ_DEV void md5_block(uint32_t st[4], const uint32_t m[16]) {
@@ -124,37 +135,26 @@ ZWZ_KERNEL md5_files_kernel(const uint8_t *__restrict__ data, const uint64_t *__
     // Software pipeline: the 64 bytes of block b+1 are loaded into registers before the 64 dependent steps of block b run,
     // so the ~1 us of HBM latency of a lane's private stream hides behind ~1 100 cycles of arithmetic. (Lanes of a warp read 32
     // different files: nothing coalesces, every block is two full 32-byte sectors per lane.)
-    if (skew == 0) {
-        uint32_t nx[16];
+    // One code path for every alignment (a warp's 32 files start at 32 unrelated addresses; a branch on the skew would run
+    // the 64-step chain twice per block): word 16 is only fetched when the file is skewed, and a funnel shift by 0 is the
+    // identity on its low operand.
+    {
+        const uint32_t sh = skew * 8u;
+        uint32_t nx[17];
+        nx[16] = 0;
         if (nblk) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) nx[k] = __ldg(w + k);
-        }
-        for (uint64_t b = 0; b < nblk; ++b) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) m[k] = nx[k];
-            w += 16;
-            if (b + 1 < nblk) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) nx[k] = __ldg(w + k);
-            }
-            md5_block(st, m);
-        }
-    } else {
-        const uint32_t sh = skew * 8u;
-        uint32_t nx[17];
-        if (nblk) {
-#pragma unroll
-            for (int k = 0; k < 17; ++k) nx[k] = __ldg(w + k); // word 16 of a block holds >= 1 valid byte because skew != 0
+            if (skew) nx[16] = __ldg(w + 16); // holds >= 1 byte of this block because skew != 0
         }
         for (uint64_t b = 0; b < nblk; ++b) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) m[k] = __funnelshift_r(nx[k], nx[k + 1], sh);
             w += 16;
             if (b + 1 < nblk) {
-                nx[0] = nx[16];
 #pragma unroll
-                for (int k = 1; k < 17; ++k) nx[k] = __ldg(w + k);
+                for (int k = 0; k < 16; ++k) nx[k] = __ldg(w + k);
+                if (skew) nx[16] = __ldg(w + 16);
             }
             md5_block(st, m);
         }
@@ -199,14 +199,15 @@ ZWZ_KERNEL md5_files_kernel(const uint8_t *__restrict__ data, const uint64_t *__
 
 // ---- large files: same one-lane-per-file chain, but the bytes arrive through shared memory -----------------------------
 // With few, long files the per-lane loads above are the problem: 32 lanes x 16 scattered words per block, every block a
-// fresh trip to HBM in front of 64 dependent steps. Here a warp copies, for each of its 32 files in turn, the next 512 bytes
-// with cp.async (32 lanes x 4 B = one coalesced 128-byte line per instruction) into a per-lane row of a double-buffered
-// staging area while all lanes hash the previous 512 bytes of their own rows. Row stride = 129 words: lane l reads word k
-// of its row from bank (l + k) mod 32 — conflict-free.
-#define ZWZ_MD5S_WARPS 2
+// fresh trip to HBM in front of 64 dependent steps. Here a CTA is two warps over the same 32 files: the LOADER warp copies,
+// for each file in turn, the next 512 bytes with cp.async (32 lanes x 4 B = one coalesced 128-byte line per instruction) into
+// a per-file row of a double-buffered staging area, while the HASHER warp's lanes digest the previous 512 bytes of their own
+// rows — nothing but the 64-step chain sits in the hasher's instruction stream. One __syncthreads per round hands the
+// buffers over. Row stride = 129 words: lane l reads word k of its row from bank (l + k) mod 32 — conflict-free.
+#define ZWZ_MD5S_THREADS 64
 #define ZWZ_MD5S_ROUND 512u                     // bytes per file per round (8 MD5 blocks)
-#define ZWZ_MD5S_ROW 129u                       // words per row (128 + 1 pad)
-#define ZWZ_MD5S_SMEM (ZWZ_MD5S_WARPS * 2u * 32u * (ZWZ_MD5S_ROW + 3u) * 4u)
+#define ZWZ_MD5S_ROW 129u                       // words per row (128 + 1 right neighbour for the funnel shift)
+#define ZWZ_MD5S_SMEM (2u * 32u * ZWZ_MD5S_ROW * 4u + 32u * 16u)
 
 #ifdef ZWZ_EMU
 ZWZ_DEV void md5s_cp4(uint32_t *dst, const uint32_t *src) { *dst = *src; }
@@ -220,20 +221,21 @@ ZWZ_DEV void md5s_commit() { asm volatile("cp.async.commit_group;" ::: "memory")
 ZWZ_DEV void md5s_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 
-// Each row holds the aligned words covering bytes [round*512, round*512 + 512 + 3] of the file's aligned stream (one extra
-// word so the funnel shift of an unaligned file has its right neighbour): 129 data words + pad.
-ZWZ_KERNEL __launch_bounds__(ZWZ_MD5S_WARPS * 32) md5_files_staged_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off,
-                                                                         const uint64_t *__restrict__ len,
-                                                                         const uint64_t *__restrict__ total_len, uint32_t *state,
-                                                                         uint8_t *digest, uint32_t n, int finalize) {
+// Each row holds the aligned words covering bytes [round*512, round*512 + 512 + 3] of the file's aligned stream.
+ZWZ_KERNEL __launch_bounds__(ZWZ_MD5S_THREADS) md5_files_staged_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off,
+                                                                      const uint64_t *__restrict__ len,
+                                                                      const uint64_t *__restrict__ total_len, uint32_t *state,
+                                                                      uint8_t *digest, uint32_t n, int finalize) {
     ZWZ_DYN_SMEM(smem);
-    const unsigned lane = lane_id(), wid = warp_id();
-    constexpr uint32_t ROWW = ZWZ_MD5S_ROW + 3u; // 132 words: 129 used, keeps rows 16-byte aligned
-    uint32_t *stage = (uint32_t *) smem + (size_t) wid * 2u * 32u * ROWW;
-    const uint32_t i = (blockIdx.x * ZWZ_MD5S_WARPS + wid) * 32u + lane;
+    const unsigned lane = lane_id();
+    const bool loader = warp_id() == 1u;
+    constexpr uint32_t ROWW = ZWZ_MD5S_ROW; // odd stride: lane l reads word k of its row from bank (l + k) mod 32
+    unsigned long long *dir = (unsigned long long *) smem; // the CTA's 32 files: aligned word pointer, readable word count
+    uint32_t *stage = (uint32_t *) (smem + 32u * 16u);     // 2 x 32 rows
+    const uint32_t i = blockIdx.x * 32u + lane;
     const bool have = i < n;
     uint32_t st[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
-    if (have && state) {
+    if (have && state && !loader) {
         st[0] = state[4 * i + 0];
         st[1] = state[4 * i + 1];
         st[2] = state[4 * i + 2];
@@ -253,46 +255,53 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_MD5S_WARPS * 32) md5_files_staged_kernel(const 
         uint64_t o = __shfl_xor_sync(ZWZ_FULL, max_rounds, d);
         max_rounds = o > max_rounds ? o : max_rounds;
     }
-    // cooperative fill of buffer `buf` with round r of all 32 files
-    auto fill = [&](uint32_t buf, uint64_t r) {
-        for (uint32_t f = 0; f < 32u; ++f) {
-            const uint32_t *fw = (const uint32_t *) __shfl_sync(ZWZ_FULL, (unsigned long long) w, (int) f);
-            const uint64_t fnw = __shfl_sync(ZWZ_FULL, (unsigned long long) nwords, (int) f);
-            const uint64_t base = r * 128u;
-            if (base >= fnw) continue; // warp-uniform
-            uint32_t *row = stage + ((size_t) buf * 32u + f) * ROWW;
-#pragma unroll
-            for (uint32_t c = 0; c < 4u; ++c) {
-                uint64_t k = base + c * 32u + lane;
-                if (k < fnw) md5s_cp4(row + c * 32u + lane, fw + k);
-            }
-            if (lane == 0 && base + 128u < fnw) md5s_cp4(row + 128u, fw + base + 128u); // right neighbour for the funnel shift
-        }
-        md5s_commit();
-    };
-    if (max_rounds) fill(0, 0);
-    for (uint64_t r = 0; r < max_rounds; ++r) {
-        md5s_wait_all();
+    if (loader) {
+        dir[2u * lane] = (unsigned long long) (uintptr_t) w;
+        dir[2u * lane + 1u] = nwords;
         __syncwarp();
-        if (r + 1 < max_rounds) fill((uint32_t) ((r + 1) & 1u), r + 1);
+        // fill buffer r & 1 with round r of all 32 files: per file 4 coalesced 128-byte lines (+ the right neighbour word)
+        for (uint64_t r = 0; r < max_rounds; ++r) {
+            const uint64_t base = r * 128u;
+            const uint32_t buf = (uint32_t) (r & 1u);
+#pragma unroll 4
+            for (uint32_t f = 0; f < 32u; ++f) {
+                const uint32_t *fw = (const uint32_t *) (uintptr_t) dir[2u * f];
+                const uint64_t fnw = dir[2u * f + 1u];
+                uint32_t *row = stage + ((size_t) buf * 32u + f) * ROWW;
+                if (base + 129u <= fnw) { // warp-uniform fast case: the whole row
+#pragma unroll
+                    for (uint32_t c = 0; c < 4u; ++c) md5s_cp4(row + c * 32u + lane, fw + base + c * 32u + lane);
+                    if (lane == 0) md5s_cp4(row + 128u, fw + base + 128u);
+                } else if (base < fnw) {
+#pragma unroll
+                    for (uint32_t c = 0; c < 4u; ++c) {
+                        uint64_t k = base + c * 32u + lane;
+                        if (k < fnw) md5s_cp4(row + c * 32u + lane, fw + k);
+                    }
+                }
+            }
+            md5s_commit();
+            md5s_wait_all();
+            __syncthreads(); // round r is in shared memory; the hasher has finished with round r - 1's buffer... (see below)
+        }
+        return;
+    }
+    // hasher: barrier r releases round r. Buffer r & 1 is refilled (with round r + 2) only after barrier r + 1, which this
+    // warp reaches after it has hashed round r.
+    const uint32_t sh = skew * 8u; // a funnel shift by 0 returns its low operand: one path for every alignment, no divergence
+    for (uint64_t r = 0; r < max_rounds; ++r) {
+        __syncthreads();
         if (r < rounds) {
             const uint32_t *row = stage + ((size_t) (r & 1u) * 32u + lane) * ROWW;
             const uint64_t b0 = r * 8u;
             const uint32_t nb = (uint32_t) (nblk - b0 < 8u ? nblk - b0 : 8u);
-            const uint32_t sh = skew * 8u;
             for (uint32_t b = 0; b < nb; ++b) {
                 uint32_t m[16];
-                if (skew == 0) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) m[k] = row[b * 16u + k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) m[k] = __funnelshift_r(row[b * 16u + k], row[b * 16u + k + 1], sh);
-                }
+                for (int k = 0; k < 16; ++k) m[k] = __funnelshift_r(row[b * 16u + k], row[b * 16u + k + 1], sh);
                 md5_block(st, m);
             }
         }
-        __syncwarp();
     }
     if (!have) return;
     if (finalize) {

@@ -9,6 +9,7 @@
 #include "zwz_common.cuh"
 #include "md5.cuh"
 #include "inflate.cuh"
+#include "inflate_lanes.cuh"
 #include "deflate_match.cuh"
 #include "deflate_encode.cuh"
 
@@ -80,6 +81,7 @@ struct zwz_ctx {
     std::string err;
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
+    int inflate_mode = 0; // 0 = by batch size, 1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
@@ -204,10 +206,12 @@ int zwz_init(int device, zwz_ctx **out) {
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<1>, zwz::MatchClass<1>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<3>, zwz::MatchClass<3>::kSmem) ||
-        zwz_rt::set_max_dyn_smem((const void *) zwz::md5_files_staged_kernel, ZWZ_MD5S_SMEM)) {
+        zwz_rt::set_max_dyn_smem((const void *) zwz::md5_files_staged_kernel, ZWZ_MD5S_SMEM) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::inflate_lanes_kernel, ZWZ_IL_SMEM)) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
+    if (const char *e = getenv("ZWZ_INFLATE_MODE")) ctx->inflate_mode = !strcmp(e, "warp") ? 1 : (!strcmp(e, "lanes") ? 2 : 0);
     if (const char *e = getenv("ZWZ_BATCH_RAW_MB")) {
         long v = atol(e);
         if (v >= 1) ctx->batch_raw_bytes = (size_t) v << 20;
@@ -591,7 +595,14 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     if (!off || !len || !raw_off || !raw_len || !status) return fail(ctx, ZWZ_E_ARG, "null argument");
     zwz_rt::set_device(ctx->device);
     zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
-    const size_t m_off = 0, m_roff = (size_t) n * 8, m_len = m_roff + (size_t) (n + 1) * 8, meta_bytes = m_len + (size_t) n * 4;
+    // Mapping: one warp per stream (inflate.cuh) when the batch is small — a warp finishes one stream sooner than a lane
+    // does — and one lane per stream (inflate_lanes.cuh) when there are enough streams to fill the GPU that way. The lane
+    // kernel keeps its Adler-32 sums unreduced and its bit counts in 32 bits, hence the size limits.
+    bool lanes = ctx->inflate_mode == 2 || (ctx->inflate_mode == 0 && n >= (uint32_t) ctx->sm_count * 3u * 32u);
+    for (uint32_t i = 0; lanes && i < n; ++i)
+        if (len[i] >= (1u << 28) || raw_off[i + 1] - raw_off[i] > (1ull << 24)) lanes = false;
+    const size_t m_off = 0, m_roff = (size_t) n * 8, m_len = m_roff + (size_t) (n + 1) * 8, m_order = m_len + (size_t) n * 4,
+                 meta_bytes = m_order + (lanes ? (size_t) n * 4 : 0);
     const size_t r_base = align_up(meta_bytes, 256);
     int rc;
     if ((rc = reserve(ctx, ctx->pin_meta, std::max(meta_bytes, (size_t) n * 8), true))) return rc;
@@ -600,6 +611,17 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     memcpy(hp + m_off, off, (size_t) n * 8);
     memcpy(hp + m_roff, raw_off, (size_t) (n + 1) * 8);
     memcpy(hp + m_len, len, (size_t) n * 4);
+    if (lanes) {
+        // streams by decreasing compressed size (counting sort on len / 32), so that the 32 lanes of a warp finish together
+        // and the longest groups start first
+        constexpr uint32_t NB = 4096;
+        std::vector<uint32_t> head(NB + 1, 0u);
+        auto bucket = [](uint32_t l) { return NB - 1u - std::min<uint32_t>(l >> 5, NB - 1u); };
+        for (uint32_t i = 0; i < n; ++i) head[bucket(len[i]) + 1]++;
+        for (uint32_t b = 0; b < NB; ++b) head[b + 1] += head[b];
+        uint32_t *order = (uint32_t *) (hp + m_order);
+        for (uint32_t i = 0; i < n; ++i) order[head[bucket(len[i])]++] = i;
+    }
     uint8_t *dm = (uint8_t *) ctx->meta.p;
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint32_t *d_rlen = (uint32_t *) (dm + r_base);
@@ -608,9 +630,16 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     if (zwz_rt::memset_device(d_counter, 0, 4, st)) return fail(ctx, ZWZ_E_CUDA, "memset failed");
     {
         ProfSpan ps(ctx, ZWZ_PROF_INFLATE, st);
-        uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * 8u);
-        ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
-                   (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags, d_counter);
+        if (lanes) {
+            uint32_t grid = std::min<uint32_t>((n + 31u) / 32u, (uint32_t) ctx->sm_count * 3u);
+            ZWZ_LAUNCH(zwz::inflate_lanes_kernel, grid, 32, ZWZ_IL_SMEM, st, d_comp, (const uint64_t *) (dm + m_off),
+                       (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat,
+                       (const uint32_t *) (dm + m_order), n, flags, d_counter);
+        } else {
+            uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * 8u);
+            ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
+                       (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags, d_counter);
+        }
     }
     if ((rc = check_launch(ctx, "inflate_kernel"))) return rc;
     if (zwz_rt::memcpy_d2h(hp, d_rlen, (size_t) n * 8, st) || zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "inflate kernel failed");
@@ -769,8 +798,7 @@ static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, cons
         const bool staged = total / n >= 65536u;
         ProfSpan ps(ctx, ZWZ_PROF_MD5, st);
         if (staged) {
-            const uint32_t per_cta = ZWZ_MD5S_WARPS * 32u;
-            ZWZ_LAUNCH(zwz::md5_files_staged_kernel, (n + per_cta - 1) / per_cta, per_cta, ZWZ_MD5S_SMEM, st, d_data, (const uint64_t *) dm,
+            ZWZ_LAUNCH(zwz::md5_files_staged_kernel, (n + 31u) / 32u, ZWZ_MD5S_THREADS, ZWZ_MD5S_SMEM, st, d_data, (const uint64_t *) dm,
                        (const uint64_t *) (dm + m_len), total_len ? (const uint64_t *) (dm + m_tot) : (const uint64_t *) nullptr,
                        state ? (uint32_t *) (dm + m_state) : (uint32_t *) nullptr, d_digest, n, finalize);
         } else {

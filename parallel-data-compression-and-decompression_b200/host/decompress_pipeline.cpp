@@ -1,11 +1,13 @@
 // decompress_pipeline.cpp — the decompress side (decompression.cpp:45-178 in the reference).
 //
 // The reference parses an archive record by record and inflates each one on the spot (one thread per archive, serial
-// inside a file), holding early records in a per-path min-heap. Here an archive is parsed into a record index first
-// (`.zwz` has no index of its own: records are self-delimiting, decompression.cpp:65-92), the reference's ordering rules
-// are applied to that index, and whole files' worth of records go to the GPU in batches (zwz_decompress_records: one
-// upload, batched inflate, device-side concatenation per file, MD5 of every output file from the same resident bytes,
-// one download).
+// inside a file), holding early records in a per-path min-heap. Here every archive is mapped and parsed into a record index
+// first (`.zwz` has no index of its own: records are self-delimiting, decompression.cpp:65-92; only the header pages are
+// touched), the reference's ordering rules are applied to that index, and whole files' worth of records form groups. W
+// workers (pipeline.hpp) each take a group: copy its payloads from the mapping into page-locked staging, make ONE trip
+// through the GPU (zwz_decompress_records: one upload, batched inflate, device-side concatenation per file, MD5 of every
+// output file from the same resident bytes, one download) and write the group's files. Console lines are emitted in group
+// order whatever W is.
 //
 // Reader rules kept from the reference:
 //   * a file receives the records with sequence ids 0, 1, 2, ... up to the first missing id (later ones would wait in
@@ -15,26 +17,28 @@
 //   * the MD5 verdict line is printed only when the record carrying is_last_chunk arrived in order and nothing was
 //     pending behind it (decompression.cpp:132) — ZWZ_VERIFY_ALL=1 prints a verdict for every complete file instead;
 //   * errors inside a stream are not fatal: whatever inflate produced is written (decompression.cpp:31).
-#include "zwz_host.hpp"
+#include "pipeline.hpp"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
 #include <fstream>
 #include <iostream>
 #include <map>
-#include <stdexcept>
+#include <sstream>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace zwzhost {
 
 namespace fs = std::filesystem;
-zwz_ctx *ctx_for(int device);
-std::string md5_of_file_on(int device, const std::string &file_path);
 
 namespace {
 
 struct Rec {
-    uint64_t off;   // payload offset inside the archive buffer
+    uint64_t off;   // payload offset inside the archive
     uint32_t len;   // payload length
     int seq;
     bool last;
@@ -48,45 +52,28 @@ struct FileState {
     bool complete = false;       // the ordered run ends with an is_last record
 };
 
-// grow-only page-locked host buffer (uploads/downloads straight from/to it run at full PCIe speed, and growing it does
-// not zero-fill gigabytes the way std::vector::resize does)
-struct PinnedBuf {
-    zwz_ctx *ctx = nullptr;
-    uint8_t *p = nullptr;
-    size_t cap = 0, len = 0;
-    explicit PinnedBuf(zwz_ctx *c) : ctx(c) {}
-    ~PinnedBuf() {
-        if (p) zwz_free_pinned(ctx, p);
-    }
-    PinnedBuf(const PinnedBuf &) = delete;
-    PinnedBuf &operator=(const PinnedBuf &) = delete;
-    void reserve(size_t n) {
-        if (n <= cap) return;
-        if (p) zwz_free_pinned(ctx, p);
-        p = nullptr;
-        cap = n + n / 8 + 4096;
-        if (zwz_malloc_pinned(ctx, cap, (void **) &p) != ZWZ_OK) throw std::runtime_error("zwz: pinned allocation failed");
-    }
-    uint8_t *data() { return p; }
+// read-only view of a mapped archive
+struct Span {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
     const uint8_t *data() const { return p; }
-    size_t size() const { return len; }
+    size_t size() const { return n; }
     uint8_t operator[](size_t i) const { return p[i]; }
 };
-
-bool read_whole(const std::string &path, PinnedBuf &buf) {
-    std::FILE *f = std::fopen(path.c_str(), "rb");
-    if (!f) return false;
-    std::fseek(f, 0, SEEK_END);
-    long n = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    buf.reserve(n > 0 ? (size_t) n : 1);
-    buf.len = n > 0 ? std::fread(buf.data(), 1, (size_t) n, f) : 0;
-    std::fclose(f);
-    return true;
-}
+struct Archive {
+    std::string filename;
+    Span bytes;
+    void *map = nullptr;
+    std::vector<FileState> files;
+};
+struct Group {
+    size_t archive = 0, first = 0, count = 0; // files [first, first + count) of that archive
+    size_t nrec = 0;
+    bool big = false; // one file whose records exceed a batch: streamed through in sub-batches
+};
 
 // decompression.cpp:65-92
-void parse_archive(const PinnedBuf &a, std::vector<FileState> &files) {
+void parse_archive(const Span &a, std::vector<FileState> &files) {
     std::map<std::string, size_t> index;
     std::map<std::string, int> expected;                 // the reference's expected_sequence_id, simulated
     std::map<std::string, std::vector<int>> pending;     // seqs sitting in the heap
@@ -159,6 +146,7 @@ void parse_archive(const PinnedBuf &a, std::vector<FileState> &files) {
     }
 }
 
+
 void ensure_parent(const std::string &file_path) {
     fs::path dir = fs::path(file_path).parent_path();
     if (!dir.empty() && !fs::exists(dir)) {
@@ -167,46 +155,90 @@ void ensure_parent(const std::string &file_path) {
     }
 }
 
-void print_verdict(const std::string &file_path, const std::string &stored, const std::string &calculated) {
+// console text of one group, released in group order
+struct Console {
+    std::ostringstream out, err;
+};
+
+void print_verdict(Console &con, RunStats &st, const std::string &file_path, const std::string &stored, const std::string &calculated) {
     if (calculated != stored) { // decompression.cpp:140-146
-        std::cerr << "MD5 mismatch for file: " << file_path << std::endl;
-        std::cout << "Expected MD5: " << stored << std::endl;
-        std::cout << "Calculated MD5: " << calculated << std::endl;
-        stats().md5_mismatch++;
+        con.err << "MD5 mismatch for file: " << file_path << "\n";
+        con.out << "Expected MD5: " << stored << "\n";
+        con.out << "Calculated MD5: " << calculated << "\n";
+        st.md5_mismatch++;
     } else {
-        std::cout << "MD5 match for file: " << file_path << std::endl;
-        stats().md5_match++;
+        con.out << "MD5 match for file: " << file_path << "\n";
+        st.md5_match++;
     }
 }
 
-// A file whose records do not fit one batch: sub-batches of consecutive records are appended to the output file and the
-// MD5 is taken the way the reference takes it — by reading the finished file back (decompression.cpp:136).
-void big_file(zwz_ctx *ctx, const PinnedBuf &arch, FileState &fsx, const std::string &output_dir, uint64_t budget, PinnedBuf &out) {
-    const RunConfig &cfg = config();
-    std::string file_path = output_dir + "/" + fsx.relpath;
-    ensure_parent(file_path);
-    std::FILE *o = std::fopen(file_path.c_str(), "wb");
-    if (!o) {
-        std::cerr << "Error creating output file: " << file_path << std::endl;
-        return;
-    }
-    const size_t per = std::max<size_t>(1, budget / CHUNK_SIZE);
-    uint64_t written = 0;
-    for (size_t r0 = 0; r0 < fsx.ordered.size(); r0 += per) {
-        size_t r1 = std::min(fsx.ordered.size(), r0 + per), nrec = r1 - r0;
-        std::vector<uint64_t> off(nrec), foff(2);
-        std::vector<uint32_t> len(nrec), cap(nrec, (uint32_t) CHUNK_SIZE), rfile(nrec, 0u), raw_len(nrec), status(nrec);
-        for (size_t i = 0; i < nrec; ++i) {
-            off[i] = fsx.ordered[r0 + i].off;
-            len[i] = fsx.ordered[r0 + i].len;
+std::mutex &stats_mu() {
+    static std::mutex mu;
+    return mu;
+}
+void merge_stats(const RunStats &s) {
+    std::lock_guard<std::mutex> lock(stats_mu());
+    RunStats &g = stats();
+    g.files += s.files;
+    g.records += s.records;
+    g.raw_bytes += s.raw_bytes;
+    g.md5_match += s.md5_match;
+    g.md5_mismatch += s.md5_mismatch;
+    g.t_read += s.t_read;
+    g.t_gpu += s.t_gpu;
+    g.t_write += s.t_write;
+}
+
+struct Job {
+    std::vector<Archive> &archives;
+    const std::vector<Group> &groups;
+    const std::string &output_dir;
+    uint64_t budget;
+    int device;
+    std::atomic<size_t> next_group{0};
+    OrderedCommit order;
+    Job(std::vector<Archive> &a, const std::vector<Group> &g, const std::string &out, uint64_t budget_, int device_)
+        : archives(a), groups(g), output_dir(out), budget(budget_), device(device_) {}
+};
+
+class Worker {
+  public:
+    Worker(Job &job, int id) : job_(job), ctx_(worker_ctx(job.device, id)), in_(ctx_), out_(ctx_) {}
+
+    void run() {
+        for (;;) {
+            size_t g = job_.next_group.fetch_add(1);
+            if (g >= job_.groups.size()) return;
+            const Group &grp = job_.groups[g];
+            Console con;
+            RunStats st;
+            if (grp.big)
+                big_file(job_.archives[grp.archive], job_.archives[grp.archive].files[grp.first], con, st);
+            else
+                small_files(grp, con, st);
+            job_.order.wait_turn(g);
+            std::string o = con.out.str(), e = con.err.str();
+            if (!o.empty()) std::cout << o << std::flush;
+            if (!e.empty()) std::cerr << e << std::flush;
+            job_.order.done(g);
+            merge_stats(st);
         }
+    }
+
+  private:
+    // inflate `nrec` records (payloads already compacted in in_) into out_, retrying with larger capacities for foreign
+    // records that inflate to more than 65 535 bytes (the reference's loop handles any size, decompression.cpp:17-33)
+    void inflate_group(std::vector<uint64_t> &off, std::vector<uint32_t> &len, std::vector<uint32_t> &rfile, uint32_t nf,
+                       std::vector<uint64_t> &foff, uint8_t *digest) {
+        const size_t nrec = off.size();
+        std::vector<uint32_t> cap(nrec, (uint32_t) CHUNK_SIZE), raw_len(nrec), status(nrec);
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
-            out.reserve(need + 64);
-            int rc = zwz_decompress_records(ctx, arch.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, 1, out.data(),
-                                            out.cap, foff.data(), raw_len.data(), status.data(), nullptr, 0);
-            if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx));
+            out_.reserve(need + 64);
+            int rc = zwz_decompress_records(ctx_, in_.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf, out_.data(),
+                                            out_.cap, foff.data(), raw_len.data(), status.data(), digest, 0);
+            if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx_));
             bool again = false;
             for (size_t i = 0; i < nrec; ++i)
                 if (status[i] == ZWZ_STREAM_OUTPUT_FULL) {
@@ -215,117 +247,195 @@ void big_file(zwz_ctx *ctx, const PinnedBuf &arch, FileState &fsx, const std::st
                 }
             if (!again || attempt >= 2) break;
         }
-        if (foff[1]) std::fwrite(out.data(), 1, (size_t) foff[1], o);
-        written += foff[1];
     }
-    std::fclose(o);
-    stats().files++;
-    stats().records += fsx.ordered.size();
-    stats().raw_bytes += written;
-    if (fsx.recs.size() != fsx.ordered.size()) std::cerr << "Warning: pending chunks remaining for file: " << fsx.relpath << std::endl;
-    if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all)) print_verdict(file_path, fsx.stored_md5, md5_of_file_on(cfg.device, file_path));
-}
 
-void decompress_zwz(const std::string &filename, const std::string &output_dir) {
-    const RunConfig &cfg = config();
-    zwz_ctx *ctx = ctx_for(cfg.device);
-    PinnedBuf arch(ctx);
-    double t0 = now_seconds();
-    if (!read_whole(filename, arch)) {
-        std::cerr << "Error opening file: " << filename << std::endl;
-        return;
+    // copies the payloads of records [r0, r1) of `recs` into in_ back to back, appending their offsets/lengths
+    void stage_payloads(const Span &arch, const std::vector<Rec> &recs, size_t r0, size_t r1, uint64_t &used, std::vector<uint64_t> &off,
+                        std::vector<uint32_t> &len) {
+        for (size_t r = r0; r < r1; ++r) {
+            std::memcpy(in_.data() + used, arch.data() + recs[r].off, recs[r].len);
+            off.push_back(used);
+            len.push_back(recs[r].len);
+            used += recs[r].len;
+        }
     }
-    std::vector<FileState> files;
-    parse_archive(arch, files);
-    stats().t_read += now_seconds() - t0;
 
-    // groups of whole files, bounded by the raw bytes they may produce
-    const uint64_t budget = std::max<uint64_t>(cfg.batch_bytes, 4 * CHUNK_SIZE);
-    PinnedBuf out(ctx);
-    size_t fi = 0;
-    while (fi < files.size()) {
-        if (files[fi].ordered.size() * CHUNK_SIZE > budget) { // one file larger than a batch: stream its records through
-            big_file(ctx, arch, files[fi], output_dir, budget, out);
-            ++fi;
-            continue;
+    void small_files(const Group &grp, Console &con, RunStats &st) {
+        Archive &a = job_.archives[grp.archive];
+        const uint32_t nf = (uint32_t) grp.count;
+        double t0 = now_seconds();
+        uint64_t comp_bytes = 0;
+        for (size_t f = grp.first; f < grp.first + grp.count; ++f)
+            for (const auto &r : a.files[f].ordered) comp_bytes += r.len;
+        in_.reserve(comp_bytes + 64);
+        std::vector<uint64_t> off, foff(nf + 1);
+        std::vector<uint32_t> len, rfile;
+        off.reserve(grp.nrec);
+        len.reserve(grp.nrec);
+        rfile.reserve(grp.nrec);
+        uint64_t used = 0;
+        for (size_t f = grp.first; f < grp.first + grp.count; ++f) {
+            stage_payloads(a.bytes, a.files[f].ordered, 0, a.files[f].ordered.size(), used, off, len);
+            rfile.insert(rfile.end(), a.files[f].ordered.size(), (uint32_t) (f - grp.first));
         }
-        size_t fj = fi;
-        uint64_t est = 0;
-        size_t nrec = 0;
-        while (fj < files.size() && (fj == fi || est + files[fj].ordered.size() * CHUNK_SIZE <= budget)) {
-            est += files[fj].ordered.size() * CHUNK_SIZE;
-            nrec += files[fj].ordered.size();
-            ++fj;
-        }
-        const uint32_t nf = (uint32_t) (fj - fi);
-        std::vector<uint64_t> off(nrec), foff(nf + 1);
-        std::vector<uint32_t> len(nrec), cap(nrec, (uint32_t) CHUNK_SIZE), rfile(nrec), raw_len(nrec), status(nrec);
-        size_t k = 0;
-        for (size_t f = fi; f < fj; ++f)
-            for (const auto &r : files[f].ordered) {
-                off[k] = r.off;
-                len[k] = r.len;
-                rfile[k] = (uint32_t) (f - fi);
-                ++k;
-            }
+        st.t_read += now_seconds() - t0;
         std::vector<uint8_t> digest((size_t) nf * 16);
         t0 = now_seconds();
-        for (int attempt = 0;; ++attempt) {
-            uint64_t need = 0;
-            for (size_t i = 0; i < nrec; ++i) need += cap[i];
-            out.reserve(need + 64);
-            int rc = zwz_decompress_records(ctx, arch.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf, out.data(),
-                                            out.cap, foff.data(), raw_len.data(), status.data(), digest.data(), 0);
-            if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx));
-            bool again = false;
-            for (size_t i = 0; i < nrec; ++i)
-                if (status[i] == ZWZ_STREAM_OUTPUT_FULL) { // a foreign record larger than 65 535 bytes: the reference's loop handles any size
-                    cap[i] = raw_len[i];
-                    again = true;
-                }
-            if (!again || attempt >= 2) break;
-        }
-        stats().t_gpu += now_seconds() - t0;
+        if (!off.empty())
+            inflate_group(off, len, rfile, nf, foff, digest.data());
+        else if (nf) // files without a single usable record: still created, and their verdict is that of the empty file
+            zwz_md5_batch(ctx_, in_.data(), foff.data(), foff.data(), nf, digest.data());
+        st.t_gpu += now_seconds() - t0;
         t0 = now_seconds();
-        for (size_t f = fi; f < fj; ++f) {
-            FileState &fsx = files[f];
-            std::string file_path = output_dir + "/" + fsx.relpath;
+        const RunConfig &cfg = config();
+        for (size_t f = grp.first; f < grp.first + grp.count; ++f) {
+            FileState &fsx = a.files[f];
+            std::string file_path = job_.output_dir + "/" + fsx.relpath;
             ensure_parent(file_path);
             std::FILE *o = std::fopen(file_path.c_str(), "wb");
             if (!o) {
-                std::cerr << "Error creating output file: " << file_path << std::endl;
+                con.err << "Error creating output file: " << file_path << "\n";
                 continue;
             }
-            uint64_t a0 = foff[f - fi], a1 = foff[f - fi + 1];
-            if (a1 > a0) std::fwrite(out.data() + a0, 1, (size_t) (a1 - a0), o);
+            uint64_t a0 = foff[f - grp.first], a1 = foff[f - grp.first + 1];
+            if (a1 > a0) std::fwrite(out_.data() + a0, 1, (size_t) (a1 - a0), o);
             std::fclose(o);
-            stats().files++;
-            stats().records += fsx.ordered.size();
-            stats().raw_bytes += a1 - a0;
-            if (fsx.recs.size() != fsx.ordered.size()) std::cerr << "Warning: pending chunks remaining for file: " << fsx.relpath << std::endl;
-            if (cfg.verbose && !fsx.stored_md5.empty()) std::cout << "Read MD5: " << fsx.stored_md5 << std::endl; // decompression.cpp:90
+            st.files++;
+            st.records += fsx.ordered.size();
+            st.raw_bytes += a1 - a0;
+            if (fsx.recs.size() != fsx.ordered.size()) con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
+            if (cfg.verbose && !fsx.stored_md5.empty()) con.out << "Read MD5: " << fsx.stored_md5 << "\n"; // decompression.cpp:90
             if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all)) {
                 char hex[32];
-                zwz_md5_hex(&digest[(f - fi) * 16], hex);
-                print_verdict(file_path, fsx.stored_md5, std::string(hex, 32));
+                zwz_md5_hex(&digest[(f - grp.first) * 16], hex);
+                print_verdict(con, st, file_path, fsx.stored_md5, std::string(hex, 32));
             }
         }
-        stats().t_write += now_seconds() - t0;
-        fi = fj;
+        st.t_write += now_seconds() - t0;
     }
+
+    // A file whose records do not fit one batch: sub-batches of consecutive records are appended to the output file and the
+    // MD5 is taken the way the reference takes it — by reading the finished file back (decompression.cpp:136).
+    void big_file(Archive &a, FileState &fsx, Console &con, RunStats &st) {
+        const RunConfig &cfg = config();
+        std::string file_path = job_.output_dir + "/" + fsx.relpath;
+        ensure_parent(file_path);
+        std::FILE *o = std::fopen(file_path.c_str(), "wb");
+        if (!o) {
+            con.err << "Error creating output file: " << file_path << "\n";
+            return;
+        }
+        const size_t per = std::max<size_t>(1, job_.budget / CHUNK_SIZE);
+        uint64_t written = 0;
+        for (size_t r0 = 0; r0 < fsx.ordered.size(); r0 += per) {
+            size_t r1 = std::min(fsx.ordered.size(), r0 + per);
+            uint64_t comp_bytes = 0;
+            for (size_t r = r0; r < r1; ++r) comp_bytes += fsx.ordered[r].len;
+            in_.reserve(comp_bytes + 64);
+            std::vector<uint64_t> off, foff(2);
+            std::vector<uint32_t> len, rfile(r1 - r0, 0u);
+            uint64_t used = 0;
+            stage_payloads(a.bytes, fsx.ordered, r0, r1, used, off, len);
+            inflate_group(off, len, rfile, 1, foff, nullptr);
+            if (foff[1]) std::fwrite(out_.data(), 1, (size_t) foff[1], o);
+            written += foff[1];
+        }
+        std::fclose(o);
+        st.files++;
+        st.records += fsx.ordered.size();
+        st.raw_bytes += written;
+        if (fsx.recs.size() != fsx.ordered.size()) con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
+        if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all))
+            print_verdict(con, st, file_path, fsx.stored_md5, md5_of_file_ctx(ctx_, file_path));
+    }
+
+    Job &job_;
+    zwz_ctx *ctx_;
+    PinnedBuf in_, out_;
+};
+
+bool map_archive(Archive &a) {
+    int fd = ::open(a.filename.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb {};
+    if (fstat(fd, &sb) != 0) {
+        ::close(fd);
+        return false;
+    }
+    a.bytes.n = (size_t) sb.st_size;
+    if (a.bytes.n) {
+        a.map = mmap(nullptr, a.bytes.n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (a.map == MAP_FAILED) {
+            a.map = nullptr;
+            ::close(fd);
+            return false;
+        }
+        a.bytes.p = (const uint8_t *) a.map;
+    }
+    ::close(fd);
+    return true;
 }
 
 } // namespace
 
-// process.hpp:40. Archives are independent; they are taken one after the other here because every one of them already
-// fills the GPU (the reference's parallelism across archives, decompression.cpp:174, was its only parallelism).
+// process.hpp:40. The reference runs one thread per archive (decompression.cpp:174); here the groups of all archives feed
+// one worker pool.
 void do_decompression(const std::string &input_dir, const std::string &output_dir) {
-    std::vector<std::string> archives;
+    const RunConfig &cfg = config();
+    std::vector<std::string> names;
     for (const auto &entry : fs::directory_iterator(input_dir)) {
-        if (entry.path().extension() == ".zwz") archives.push_back(entry.path().string()); // decompression.cpp:168-172
+        if (entry.path().extension() == ".zwz") names.push_back(entry.path().string()); // decompression.cpp:168-172
     }
-    std::sort(archives.begin(), archives.end());
-    for (const auto &a : archives) decompress_zwz(a, output_dir);
+    std::sort(names.begin(), names.end());
+
+    double t0 = now_seconds();
+    std::vector<Archive> archives;
+    archives.reserve(names.size());
+    for (const auto &n : names) {
+        Archive a;
+        a.filename = n;
+        if (!map_archive(a)) {
+            std::cerr << "Error opening file: " << n << std::endl;
+            continue;
+        }
+        parse_archive(a.bytes, a.files);
+        archives.push_back(std::move(a));
+    }
+    // groups of whole files, bounded by the raw bytes they may produce
+    const uint64_t budget = std::max<uint64_t>(cfg.batch_bytes, 4 * CHUNK_SIZE);
+    std::vector<Group> groups;
+    for (size_t ai = 0; ai < archives.size(); ++ai) {
+        const auto &files = archives[ai].files;
+        size_t fi = 0;
+        while (fi < files.size()) {
+            if (files[fi].ordered.size() * CHUNK_SIZE > budget) {
+                groups.push_back({ai, fi, 1, files[fi].ordered.size(), true});
+                ++fi;
+                continue;
+            }
+            size_t fj = fi, nrec = 0;
+            uint64_t est = 0;
+            while (fj < files.size() && (fj == fi || est + files[fj].ordered.size() * CHUNK_SIZE <= budget) &&
+                   files[fj].ordered.size() * CHUNK_SIZE <= budget) {
+                est += files[fj].ordered.size() * CHUNK_SIZE;
+                nrec += files[fj].ordered.size();
+                ++fj;
+            }
+            groups.push_back({ai, fi, fj - fi, nrec, false});
+            fi = fj;
+        }
+    }
+    stats().t_read += now_seconds() - t0;
+
+    Job job(archives, groups, output_dir, budget, cfg.device);
+    const int workers = (int) std::min<size_t>((size_t) worker_count(), std::max<size_t>(1, groups.size()));
+    if (!groups.empty())
+        run_workers(workers, job.order, [&](int w) {
+            Worker worker(job, w);
+            worker.run();
+        });
+    for (auto &a : archives)
+        if (a.map) munmap(a.map, a.bytes.n);
     print_timing("decompress");
 }
 

@@ -29,13 +29,30 @@ double now_seconds() {
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
 }
-void print_timing(const char *what) {
+static double g_t0 = now_seconds();
+int timing_level() {
     const char *e = std::getenv("ZWZ_TIMING");
-    if (!e || !*e || *e == '0') return;
+    return (e && *e) ? std::atoi(e) : 0;
+}
+void timing_mark(const char *what) { // ZWZ_TIMING>=1: seconds since the process started, at a named point
+    if (timing_level() >= 1) std::cerr << "[zwz timing] t+" << now_seconds() - g_t0 << " s: " << what << std::endl;
+}
+zwz_ctx *ctx_for(int device);
+void print_timing(const char *what) {
+    if (timing_level() < 1) return;
     const RunStats &s = stats();
     std::cerr << "[zwz timing] " << what << ": init " << s.t_init << " s, read/parse " << s.t_read << " s, gpu passes " << s.t_gpu
               << " s, write " << s.t_write << " s; " << s.files << " files, " << s.records << " records, " << s.raw_bytes << " raw bytes"
               << std::endl;
+    if (timing_level() >= 2) { // per-kernel device time (events around every launch; enabled in ctx_for)
+        double ms[ZWZ_PROF_N];
+        uint64_t launches[ZWZ_PROF_N];
+        if (zwz_profile_read(ctx_for(config().device), ms, launches, 0) == ZWZ_OK)
+            std::cerr << "[zwz timing] kernels (ms/launches): match " << ms[ZWZ_PROF_MATCH] << "/" << launches[ZWZ_PROF_MATCH] << ", encode "
+                      << ms[ZWZ_PROF_ENCODE] << "/" << launches[ZWZ_PROF_ENCODE] << ", inflate " << ms[ZWZ_PROF_INFLATE] << "/"
+                      << launches[ZWZ_PROF_INFLATE] << ", md5 " << ms[ZWZ_PROF_MD5] << "/" << launches[ZWZ_PROF_MD5] << ", pack/gather "
+                      << ms[ZWZ_PROF_PACK] << "/" << launches[ZWZ_PROF_PACK] << std::endl;
+    }
 }
 
 static int env_int(const char *name, int dflt) {

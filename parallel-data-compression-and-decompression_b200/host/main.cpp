@@ -53,6 +53,7 @@ static void compress(const std::string &folder_path, const std::string &output_p
         }
     }
     std::cout << "file_record: " << file_record << std::endl;
+    timing_mark("file record ready");
     int file_count = count_non_empty_lines(file_record);
     if (cfg.world_rank < file_count) {
         do_compression(folder_path, output_path, file_record, cfg.world_rank);
@@ -77,6 +78,7 @@ int main(int argc, char *argv[]) {
     double start_time = now_s();
     config_from_env();
     RunConfig &cfg = config();
+    timing_mark("configured (CUDA runtime initialised)");
 
     if (argc < 4) { // main.cpp:88-92
         std::cerr << "Usage: " << argv[0] << " <compress/decompress> <source directory path> <output directory path>\n";
@@ -139,6 +141,7 @@ int main(int argc, char *argv[]) {
         std::cerr << "Rank: " << cfg.world_rank << " - fatal: " << e.what() << std::endl;
         rc = 2;
     }
+    timing_mark("operation finished");
     if (self_gpus > 1 && cfg.world_rank != 0) _exit(rc);
     for (pid_t k : kids) {
         int st = 0;

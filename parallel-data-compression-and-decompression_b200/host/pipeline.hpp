@@ -1,0 +1,105 @@
+// pipeline.hpp — the worker pool both host pipelines share (internal to the host library).
+//
+// The reference overlaps nothing on the compress side but producer/consumer hand-off (compression.cpp:160-194) and runs one
+// thread per archive on the decompress side (decompression.cpp:174). Here a rank keeps W workers (ZWZ_WORKERS, default 3),
+// each with its own zwz_ctx — its own CUDA stream, device arenas and page-locked staging — and every worker takes whole
+// batches through read -> GPU -> write on its own. Kernels of different workers overlap on the device (the MD5 of a few long
+// files is a serial chain that occupies a handful of SMs for ~100 ms; the other workers' deflate/inflate kernels fill the
+// rest of the GPU meanwhile), copies overlap kernels, and file I/O overlaps both. Results are committed in batch order, so
+// the archive bytes and the console output do not depend on W or on timing.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+
+#include "zwz_host.hpp"
+
+namespace zwzhost {
+
+zwz_ctx *ctx_for(int device);
+zwz_ctx *worker_ctx(int device, int worker); // worker 0 shares ctx_for(device); the others get their own, created on first use
+int worker_count();                          // ZWZ_WORKERS, clamped to [1, 8]
+std::string md5_of_file_ctx(zwz_ctx *ctx, const std::string &file_path);
+
+// batch b may commit only after batches 0..b-1 have
+class OrderedCommit {
+  public:
+    void wait_turn(size_t index) {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [&] { return next_ == index || aborted_; });
+        if (aborted_) throw std::runtime_error("zwz: pipeline aborted");
+    }
+    void done(size_t index) {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            if (next_ == index) next_ = index + 1;
+        }
+        cv_.notify_all();
+    }
+    void abort() {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            aborted_ = true;
+        }
+        cv_.notify_all();
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    size_t next_ = 0;
+    bool aborted_ = false;
+};
+
+// runs body(worker_id) on n threads (n == 1: on the caller's thread); the first exception is rethrown on the caller
+inline void run_workers(int n, OrderedCommit &order, const std::function<void(int)> &body) {
+    if (n <= 1) {
+        body(0);
+        return;
+    }
+    std::exception_ptr first;
+    std::mutex mu;
+    std::vector<std::thread> threads;
+    for (int w = 0; w < n; ++w)
+        threads.emplace_back([&, w] {
+            try {
+                body(w);
+            } catch (...) {
+                {
+                    std::lock_guard<std::mutex> lock(mu);
+                    if (!first) first = std::current_exception();
+                }
+                order.abort();
+            }
+        });
+    for (auto &t : threads) t.join();
+    if (first) std::rethrow_exception(first);
+}
+
+// grow-only page-locked host buffer (copies from/to it run at full PCIe speed and asynchronously)
+struct PinnedBuf {
+    zwz_ctx *ctx = nullptr;
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    explicit PinnedBuf(zwz_ctx *c) : ctx(c) {}
+    ~PinnedBuf() {
+        if (p) zwz_free_pinned(ctx, p);
+    }
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) zwz_free_pinned(ctx, p);
+        p = nullptr;
+        cap = n + n / 8 + 4096;
+        if (zwz_malloc_pinned(ctx, cap, (void **) &p) != ZWZ_OK) throw std::runtime_error("zwz: pinned allocation failed");
+    }
+    uint8_t *data() { return p; }
+};
+
+} // namespace zwzhost

@@ -1,7 +1,8 @@
 // verify.cpp — md5_of_file (verification.cpp:6-30) on the GPU, and the process-wide zwz_ctx.
-#include "zwz_host.hpp"
+#include "pipeline.hpp"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -25,20 +26,45 @@ zwz_ctx *ctx_for(int device) {
         std::cerr << "zwz: cannot initialise CUDA device " << device << " (error " << rc << "); there is no CPU fallback" << std::endl;
         throw std::runtime_error("zwz_init failed");
     }
+    if (timing_level() >= 2) zwz_profile_enable(c, 1);
     all[device] = c;
     return c;
+}
+
+// the extra contexts of the worker pool (pipeline.hpp): cheap once the device's primary context exists
+zwz_ctx *worker_ctx(int device, int worker) {
+    if (worker <= 0) return ctx_for(device);
+    ctx_for(device); // the first initialisation of the device is the slow one: do it once, outside the lock below
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, zwz_ctx *> all;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(device, worker);
+    auto it = all.find(key);
+    if (it != all.end()) return it->second;
+    zwz_ctx *c = nullptr;
+    if (zwz_init(device, &c) != ZWZ_OK || !c) throw std::runtime_error("zwz_init failed for a worker context");
+    if (timing_level() >= 2) zwz_profile_enable(c, 1);
+    all[key] = c;
+    return c;
+}
+
+int worker_count() {
+    const char *e = std::getenv("ZWZ_WORKERS");
+    int w = (e && *e) ? std::atoi(e) : 3;
+    return w < 1 ? 1 : (w > 8 ? 8 : w);
 }
 
 // Streams the file through the device in pieces (the reference streams 1 024-byte reads through MD5_Update,
 // verification.cpp:15-19; the update granularity does not change the digest). Returns "" if the file cannot be opened,
 // like the reference (verification.cpp:8-11).
-std::string md5_of_file_on(int device, const std::string &file_path) {
+std::string md5_of_file_on(int device, const std::string &file_path) { return md5_of_file_ctx(ctx_for(device), file_path); }
+
+std::string md5_of_file_ctx(zwz_ctx *ctx, const std::string &file_path) {
     FILE *f = std::fopen(file_path.c_str(), "rb");
     if (!f) {
         std::cerr << "Cannot open file: " << file_path << std::endl;
         return "";
     }
-    zwz_ctx *ctx = ctx_for(device);
     const size_t piece = (size_t) 64 << 20; // multiple of 64
     void *pin = nullptr, *dev = nullptr;
     if (zwz_malloc_pinned(ctx, piece, &pin) != ZWZ_OK || zwz_malloc_device(ctx, piece + 64, &dev) != ZWZ_OK) {

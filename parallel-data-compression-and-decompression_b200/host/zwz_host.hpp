@@ -37,7 +37,7 @@ struct RunConfig {
     int level = 0;            // 0 = library default
     bool verbose = false;     // per-file lines like the reference prints (compression.cpp:100, decompression.cpp:90,145)
     bool verify_all = false;  // also print an MD5 verdict for files whose last record arrived out of order
-    std::size_t batch_bytes = (std::size_t) 256 << 20;
+    std::size_t batch_bytes = (std::size_t) 128 << 20; // per worker (ZWZ_BATCH_MB)
 };
 RunConfig &config();
 void config_from_env();
@@ -51,6 +51,8 @@ struct RunStats {
 };
 double now_seconds();
 void print_timing(const char *what);
+void timing_mark(const char *what);
+int timing_level();
 RunStats &stats();
 
 } // namespace zwzhost

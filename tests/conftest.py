@@ -45,6 +45,52 @@ def ctx(request):
     return request.getfixturevalue("emu_ctx")
 
 
+def _with_mode(make, mode):
+    old = os.environ.get("ZWZ_INFLATE_MODE")
+    os.environ["ZWZ_INFLATE_MODE"] = mode  # read once, by zwz_init
+    try:
+        return make()
+    finally:
+        if old is None:
+            del os.environ["ZWZ_INFLATE_MODE"]
+        else:
+            os.environ["ZWZ_INFLATE_MODE"] = old
+
+
+@pytest.fixture(scope="session")
+def cuda_ctx_lanes():
+    ctx = _with_mode(_cuda_context, "lanes")
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
+def cuda_ctx_warp():
+    ctx = _with_mode(_cuda_context, "warp")
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
+def emu_ctx_lanes():
+    import emu_lib
+    ctx = _with_mode(emu_lib.emu_context, "lanes")
+    yield ctx
+    ctx.close()
+
+
+# The two inflate mappings (one warp per stream / one lane per stream) are picked by batch size in production; the inflate
+# tests force each of them on the same inputs.
+INFLATE_BACKENDS = [pytest.param("emu_ctx", id="emu-warp"), pytest.param("emu_ctx_lanes", id="emu-lanes"),
+                    pytest.param("cuda_ctx_warp", id="cuda-warp", marks=pytest.mark.gpu),
+                    pytest.param("cuda_ctx_lanes", id="cuda-lanes", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=INFLATE_BACKENDS)
+def ctx_inf(request):
+    return request.getfixturevalue(request.param)
+
+
 @pytest.fixture
 def is_gpu(request):
     return "cuda" in request.node.name

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 namespace simt {
@@ -185,6 +186,10 @@ zwz_simt_switch:
 )");
 
 void launch(unsigned grid, unsigned block, size_t smem_bytes, std::function<void()> body) {
+    // one kernel at a time: the emulator's state (fibers, threadIdx, `__shared__` statics) is process-wide, and a host with
+    // several worker threads (each with its own zwz_ctx) may launch concurrently
+    static std::mutex launch_mu;
+    std::lock_guard<std::mutex> launch_lock(launch_mu);
     State &s = st();
     if (block == 0 || block > 1024) die("bad block size");
     if (s.fibers.size() < block) {

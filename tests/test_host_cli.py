@@ -176,6 +176,14 @@ def test_self_round_trip_and_multi_batch(main_bin, tmp_path):
     log = run([main_bin, "decompress", arch, out], {"ZWZ_BATCH_MB": "1"})
     assert log.count("MD5 match for file") == len(specs) and "mismatch" not in log
     same_tree(str(src), out)
+    # the worker pool (host/pipeline.hpp) commits batches in order: same archive bytes and same console lines for any W
+    arch1, out1 = str(tmp_path / "arch1"), str(tmp_path / "out1")
+    run([main_bin, "compress", str(src), arch1], {"ZWZ_BATCH_MB": "1", "ZWZ_WORKERS": "1"})
+    assert filecmp.cmp(os.path.join(arch, "compressed_0.zwz"), os.path.join(arch1, "compressed_0.zwz"), shallow=False)
+    log1 = run([main_bin, "decompress", arch1, out1], {"ZWZ_BATCH_MB": "1", "ZWZ_WORKERS": "1"})
+    verdicts = lambda t, o: [l.replace(o, "") for l in t.splitlines() if l.startswith("MD5 match")]  # noqa: E731
+    assert verdicts(log, out) == verdicts(log1, out1)
+    same_tree(str(src), out1)
 
 
 def test_usage_and_errors(main_bin, tmp_path):

@@ -111,15 +111,15 @@ def _check_inflate(ctx, streams, cap):
         assert got == O.ref_inflate_chunk(s)[:cap]  # and the reference's own zlib loop says the same
 
 
-def test_inflate_all_block_types(ctx, is_gpu):
+def test_inflate_all_block_types(ctx_inf, is_gpu):
     sizes = [("T", 65535), ("S", 40000), ("B", 65535), ("R", 65535), ("J", 7000), ("T", 96), ("T", 0), ("T", 1)]
     if not is_gpu:
         sizes = [("T", 30000), ("S", 9000), ("B", 12000), ("R", 3000), ("J", 2000), ("T", 96), ("T", 0), ("T", 1)]
     streams = [c for _, c in _zlib_streams(sizes)]
-    _check_inflate(ctx, streams, 70000)
+    _check_inflate(ctx_inf, streams, 70000)
 
 
-def test_inflate_truncated_and_corrupted(ctx, is_gpu):
+def test_inflate_truncated_and_corrupted(ctx_inf, is_gpu):
     rng = random.Random(7)
     sizes = [("T", 20000), ("S", 9000), ("B", 9000), ("R", 3000), ("T", 50)] if not is_gpu else [("T", 65535), ("S", 40000), ("B", 65535), ("R", 30000), ("T", 50)]
     cases = []
@@ -132,31 +132,31 @@ def test_inflate_truncated_and_corrupted(ctx, is_gpu):
                 cb[rng.randrange(len(cb))] ^= 1 << rng.randrange(8)
             cases.append(bytes(cb))
     cases += [b"", b"\x78", b"\x78\x9c", b"\x78\x9c\x03", b"\x78\x9d\x03\x00", b"\x00" * 10, b"\xff" * 10, b"\x78\x9c\x07"]
-    _check_inflate(ctx, cases, 70000)
+    _check_inflate(ctx_inf, cases, 70000)
 
 
-def test_inflate_output_capacity(ctx):
+def test_inflate_output_capacity(ctx_inf):
     raw = corpus.gen_text(9000, 596, 3).tobytes()
     streams = [zlib.compress(raw), zlib.compress(raw[:100]), zlib.compress(b"")]
     comp, off = _cat(streams)
     raw_off = np.array([0, 1000, 1100, 1100], dtype=np.uint64)
-    out, rl, st = ctx.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
+    out, rl, st = ctx_inf.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
     assert list(st) == [O.STREAM_OUTPUT_FULL, O.STREAM_END, O.STREAM_END]
     assert list(rl) == [9000, 100, 0]
     assert out[:1000].tobytes() == raw[:1000] and out[1000:1100].tobytes() == raw[:100]
 
 
-def test_inflate_reference_truncated_record(ctx):
+def test_inflate_reference_truncated_record(ctx_inf):
     """Interop with the reference's defect: its 65 535-byte truncated payload inflates to 65 513 bytes."""
     r = corpus.gen_random(CHUNK, 596, 1).tobytes()
     c = O.ref_deflate_chunk(r)
     assert len(c) == CHUNK
-    out, rl, st = ctx.inflate_batch(c, [0], [len(c)], [0, 70000])
+    out, rl, st = ctx_inf.inflate_batch(c, [0], [len(c)], [0, 70000])
     assert int(rl[0]) == 65513 and int(st[0]) == O.STREAM_TRUNCATED and out[:65513].tobytes() == r[:65513]
 
 
 @pytest.mark.parametrize("name", ["edge_r1", "edge_r2", "foreign"])
-def test_inflate_golden_reference_archives(ctx, name, is_gpu):
+def test_inflate_golden_reference_archives(ctx_inf, name, is_gpu):
     """Criterion (2): archives written by the unmodified reference binary inflate to the bytes the reference's own
     decompress wrote (tests/golden/manifest.json)."""
     man = json.load(open(os.path.join(GOLD, "manifest.json")))
@@ -177,7 +177,7 @@ def test_inflate_golden_reference_archives(ctx, name, is_gpu):
     comp, off = _cat([r.payload for r in recs])
     cap = 1 << 20 if name == "foreign" else 65536
     raw_off = np.arange(len(recs) + 1, dtype=np.uint64) * np.uint64(cap)
-    out, rl, st = ctx.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
+    out, rl, st = ctx_inf.inflate_batch(comp, off[:-1], np.diff(off).astype(np.uint32), raw_off)
     files = {}
     for i, r in enumerate(recs):
         assert int(rl[i]) <= cap
@@ -186,6 +186,37 @@ def test_inflate_golden_reference_archives(ctx, name, is_gpu):
         data = b"".join(parts[s] for s in sorted(parts))
         want = man[name]["outputs"][path]
         assert (len(data), hashlib.md5(data).hexdigest()) == (want["size"], want["md5"]), path
+
+
+def test_inflate_own_streams_both_mappings(ctx_inf, is_gpu):
+    """Streams written by this repo's encoder (multi-block dynamic, fixed, stored, the two-record split) through both inflate
+    mappings; 70 streams of mixed sizes so that the lanes of a warp sit in different states and park at different times."""
+    n = 70 if not is_gpu else 3000
+    rng = np.random.default_rng(11)
+    chunks = []
+    for i in range(n):
+        c = "TSJBRI"[i % 6]
+        ln = int(rng.integers(0, 12000 if not is_gpu else CHUNK + 1))
+        if i % 17 == 0:
+            ln = CHUNK if is_gpu else 20000
+        chunks.append(corpus.gen_file(c, ln, 596, 4000 + i).tobytes())
+    raw, off = _cat(chunks)
+    packed, poff, res = ctx_inf.deflate_batch(raw, off[:-1], np.diff(off).astype(np.uint32))
+    streams = []
+    for i in range(n):
+        p = packed[int(poff[i]):int(poff[i + 1])].tobytes()
+        l0 = int(res["len0"][i])
+        streams += [(i, p[:l0])] + ([(i, p[l0:])] if int(res["len1"][i]) else [])
+    comp, coff = _cat([s for _, s in streams])
+    cap = 65536
+    raw_off = np.arange(len(streams) + 1, dtype=np.uint64) * np.uint64(cap)
+    out, rl, st = ctx_inf.inflate_batch(comp, coff[:-1], np.diff(coff).astype(np.uint32), raw_off)
+    assert (st == O.STREAM_END).all()
+    got = {}
+    for k, (i, _) in enumerate(streams):
+        got[i] = got.get(i, b"") + out[int(raw_off[k]):int(raw_off[k]) + int(rl[k])].tobytes()
+    for i in range(n):
+        assert got[i] == chunks[i], i
 
 
 def test_decompress_records_group_stress(ctx, is_gpu):

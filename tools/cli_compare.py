@@ -98,11 +98,11 @@ def main():
         ngpu = max(1, torch.cuda.device_count())
         our_ranks = min(a.ranks, ngpu)
         t, outs = run_ranks(MAIN, ["compress", src, our_arch], our_ranks,
-                            lambda r: {"ZWZ_WORLD": str(our_ranks), "ZWZ_RANK": str(r), "ZWZ_TIMING": "1"})
+                            lambda r: {"ZWZ_WORLD": str(our_ranks), "ZWZ_RANK": str(r), "ZWZ_TIMING": os.environ.get("ZWZ_TIMING", "1")})
         res["our_compress_s"], res["our_ranks"] = t, our_ranks
         res["our_compress_phases"] = [l for o in outs for l in o.splitlines() if "[zwz timing]" in l]
         our_out = os.path.join(tmp, "our_out")
-        t, outs = run_ranks(MAIN, ["decompress", our_arch, our_out], 1, lambda r: {"ZWZ_TIMING": "1"})
+        t, outs = run_ranks(MAIN, ["decompress", our_arch, our_out], 1, lambda r: {"ZWZ_TIMING": os.environ.get("ZWZ_TIMING", "1")})
         res["our_decompress_s"] = t
         res["our_decompress_phases"] = [l for o in outs for l in o.splitlines() if "[zwz timing]" in l]
         res["our_archive_bytes"] = du(our_arch)
