@@ -49,11 +49,22 @@ struct EncWarpSmem {
     uint32_t stage[64];     // bit sink staging window
     uint32_t misc[8];
 };
+#define ZWZ_DE_SMEM (ZWZ_DE_WARPS * (uint32_t) sizeof(zwz::EncWarpSmem))
+
+// The warp's slice of the CTA's (dynamic) shared memory. The out-of-line helpers below fetch it themselves instead of taking
+// a reference, so that the compiler still knows the address space (a reference parameter would turn every access into a
+// generic load). They are out of line on purpose: fully inlined, this kernel was 345 KB of SASS — three copies of the block
+// emitter, nine of the Huffman construction — and with 24 warps per SM in different phases the dominant stall was
+// instruction fetch (`no_instruction`, profiles/round1_notes.md).
+ZWZ_DEV EncWarpSmem &enc_smem() {
+    ZWZ_DYN_SMEM(enc_raw);
+    return ((EncWarpSmem *) enc_raw)[warp_id()];
+}
 
 // -------------------------------------------------------------------------------------------------------------------
 // Length-limited Huffman code for the `nsym` symbols whose counts are freq[0..nsym). Writes blen[] and code[].
 // -------------------------------------------------------------------------------------------------------------------
-ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, uint32_t maxbits, uint8_t *blen, uint32_t *code) {
+ZWZ_DEV void enc_huffman_body(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, uint32_t maxbits, uint8_t *blen, uint32_t *code) {
     const unsigned lane = lane_id();
     // 1. compact used symbols into keys
     uint32_t nused = 0;
@@ -205,6 +216,15 @@ ZWZ_DEV void enc_huffman(EncWarpSmem &S, const uint32_t *freq, uint32_t nsym, ui
 // -------------------------------------------------------------------------------------------------------------------
 // bit sink: warp-collective append of (bits, nbits <= 57) per lane, in lane order
 // -------------------------------------------------------------------------------------------------------------------
+// which: 0 = literal/length, 1 = distance, 2 = code-length alphabet
+ZWZ_DEV_NOINLINE void enc_huffman(uint32_t which) {
+    EncWarpSmem &S = enc_smem();
+    const uint32_t *freq = which == 0u ? S.freq : (which == 1u ? S.freq + ZWZ_DE_DOFF : S.clfreq);
+    uint8_t *blen = which == 0u ? S.blen : (which == 1u ? S.blen + ZWZ_DE_DOFF : S.clblen);
+    uint32_t *code = which == 0u ? S.code : (which == 1u ? S.code + ZWZ_DE_DOFF : S.clcode);
+    enc_huffman_body(S, freq, which == 0u ? ZWZ_DE_LL : (which == 1u ? ZWZ_DE_D : 19u), which == 2u ? 7u : 15u, blen, code);
+}
+
 struct BitSink {
     uint32_t *outw;     // 4-byte aligned output words
     uint32_t nwords;    // words already produced (counted even when they no longer fit)
@@ -254,7 +274,7 @@ ZWZ_DEV uint32_t sink_finish(EncWarpSmem &S, BitSink &k) {
     return k.nwords * 4u + ((k.fill + 7u) >> 3);
 }
 
-ZWZ_DEV uint32_t enc_adler_global(const uint8_t *p, uint32_t n) {
+ZWZ_DEV_NOINLINE uint32_t enc_adler_global(const uint8_t *p, uint32_t n) {
     uint64_t s0 = 0, s1 = 0;
     for (uint32_t j = lane_id(); j < n; j += 32u) {
         uint32_t v = p[j];
@@ -270,7 +290,7 @@ ZWZ_DEV uint32_t enc_adler_global(const uint8_t *p, uint32_t n) {
 }
 
 // one complete zlib stream with a single stored block; returns its size
-ZWZ_DEV uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, uint32_t n, uint32_t adler) {
+ZWZ_DEV_NOINLINE uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, uint32_t n, uint32_t adler) {
     const unsigned lane = lane_id();
     if (lane == 0) {
         out[0] = 0x78;
@@ -290,7 +310,10 @@ ZWZ_DEV uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, uint32_t n,
 }
 
 // histogram of the tokens [t0, t1) into freq[0..320) (literal/length at 0, distance at 288); returns their extra bits
-ZWZ_DEV uint64_t enc_hist_tokens(const uint32_t *m, uint32_t t0, uint32_t t1, uint32_t *freq) {
+// into_code: histogram into S.code (free between two Huffman builds) instead of S.freq
+ZWZ_DEV_NOINLINE uint64_t enc_hist_tokens(const uint32_t *m, uint32_t t0, uint32_t t1, bool into_code) {
+    EncWarpSmem &S = enc_smem();
+    uint32_t *freq = into_code ? S.code : S.freq;
     const unsigned lane = lane_id();
     for (uint32_t i = lane; i < 320u; i += 32u) freq[i] = 0;
     __syncwarp();
@@ -315,7 +338,12 @@ ZWZ_DEV uint64_t enc_hist_tokens(const uint32_t *m, uint32_t t0, uint32_t t1, ui
 }
 
 // empirical entropy (bits) of the two alphabets in a[0..320) (+ b[0..320) when b != nullptr), and the used-symbol count
-ZWZ_DEV float enc_entropy_bits(const uint32_t *a, const uint32_t *b, uint32_t &nused_out) {
+// sel: 0 = S.freq, 1 = S.code (a second histogram), 2 = their sum
+ZWZ_DEV_NOINLINE float enc_entropy_bits(uint32_t sel, uint32_t *nused_ptr) {
+    EncWarpSmem &S = enc_smem();
+    const uint32_t *a = sel == 1u ? S.code : S.freq;
+    const uint32_t *b = sel == 2u ? S.code : nullptr;
+    uint32_t nused_out;
     const unsigned lane = lane_id();
     float nl = 0.f, nd = 0.f, h = 0.f;
     uint32_t nused = 0;
@@ -336,17 +364,18 @@ ZWZ_DEV float enc_entropy_bits(const uint32_t *a, const uint32_t *b, uint32_t &n
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(ZWZ_FULL, h, d);
     nused_out = warp_sum(nused);
+    *nused_ptr = nused_out;
     return h;
 }
 
 // One DEFLATE block over the tokens [t0, t1): S.freq must hold their histogram (without the end-of-block symbol).
 // Builds the three Huffman codes, picks fixed or dynamic (whichever is smaller) and appends the block to the sink.
-ZWZ_DEV void enc_emit_block(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint32_t t0, uint32_t t1, uint64_t extra_bits, bool last) {
+ZWZ_DEV void enc_emit_block_body(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint32_t t0, uint32_t t1, uint64_t extra_bits, bool last) {
     const unsigned lane = lane_id();
     if (lane == 0) S.freq[256] += 1u; // end of block
     __syncwarp();
-    enc_huffman(S, S.freq, ZWZ_DE_LL, 15u, S.blen, S.code);
-    enc_huffman(S, S.freq + ZWZ_DE_DOFF, ZWZ_DE_D, 15u, S.blen + ZWZ_DE_DOFF, S.code + ZWZ_DE_DOFF);
+    enc_huffman(0u);
+    enc_huffman(1u);
     __syncwarp();
 
     // HLIT / HDIST: highest used symbol + 1
@@ -409,7 +438,7 @@ ZWZ_DEV void enc_emit_block(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint3
     }
     __syncwarp();
     ncl = S.misc[0];
-    enc_huffman(S, S.clfreq, 19u, 7u, S.clblen, S.clcode);
+    enc_huffman(2u);
     __syncwarp();
     // HCLEN: last used entry in the transmission order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
     uint32_t ord = lane < 3u ? 16u + lane : (lane == 3u ? 0u : ((lane & 1u) ? 7u - ((lane - 5u) >> 1) : 8u + ((lane - 4u) >> 1)));
@@ -513,6 +542,13 @@ ZWZ_DEV void enc_emit_block(EncWarpSmem &S, BitSink &k, const uint32_t *m, uint3
     }
 }
 
+// out of line (once per DEFLATE block): the sink travels through memory, the body works on a register copy
+ZWZ_DEV_NOINLINE void enc_emit_block(BitSink *kp, const uint32_t *m, uint32_t t0, uint32_t t1, uint64_t extra_bits, bool last) {
+    BitSink k = *kp;
+    enc_emit_block_body(enc_smem(), k, m, t0, t1, extra_bits, last);
+    *kp = k;
+}
+
 ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     const unsigned lane = lane_id();
     const uint32_t n = job.raw_len[c];
@@ -533,7 +569,7 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         if (lane == 0) S.freq[256] = 1u;
         __syncwarp();
         uint32_t nu;
-        const float hb = enc_entropy_bits(S.freq, nullptr, nu);
+        const float hb = enc_entropy_bits(0u, &nu);
         const float bound_bytes = hb * 0.125f + 7.f + (float) (nu >> 2);
         if (bound_bytes * 0.9995f >= (float) (n + 11u) - (float) (n >> 8) && n + 11u <= ZWZ_CHUNK) {
             uint32_t l0 = enc_stored_stream(out, src, n, job.adler[c]);
@@ -662,19 +698,19 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     // base blocks of equal size, about ZWZ_DE_BASE tokens each (a short tail block would pay a whole header for nothing)
     const uint32_t nbase = (ntok + ZWZ_DE_BASE / 2u) / ZWZ_DE_BASE;
     if (nbase <= 1u) {
-        enc_emit_block(S, k, m, 0, ntok, extra_bits, true); // S.freq still holds the whole-chunk histogram from the parse
+        enc_emit_block(&k, m, 0, ntok, extra_bits, true); // S.freq still holds the whole-chunk histogram from the parse
     } else {
         const uint32_t bsz = (ntok + nbase - 1u) / nbase;
         uint32_t t0 = 0, t1 = bsz;
-        uint64_t xb = enc_hist_tokens(m, t0, t1, S.freq);
+        uint64_t xb = enc_hist_tokens(m, t0, t1, false);
         while (t1 < ntok) {
             const uint32_t t2 = t1 + bsz < ntok ? t1 + bsz : ntok;
             uint32_t *nf = S.code; // free until the next Huffman build
-            const uint64_t xn = enc_hist_tokens(m, t1, t2, nf);
+            const uint64_t xn = enc_hist_tokens(m, t1, t2, true);
             uint32_t ua, ub, uab;
-            const float ha = enc_entropy_bits(S.freq, nullptr, ua);
-            const float hb = enc_entropy_bits(nf, nullptr, ub);
-            const float hab = enc_entropy_bits(S.freq, nf, uab);
+            const float ha = enc_entropy_bits(0u, &ua);
+            const float hb = enc_entropy_bits(1u, &ub);
+            const float hab = enc_entropy_bits(2u, &uab);
             const float sep = ha + hb + 200.f + 4.f * (float) (ua + ub);
             const float mer = hab + 100.f + 4.f * (float) uab;
             if (mer <= sep) {
@@ -683,13 +719,13 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
                 xb += xn;
                 t1 = t2;
             } else {
-                enc_emit_block(S, k, m, t0, t1, xb, false);
+                enc_emit_block(&k, m, t0, t1, xb, false);
                 t0 = t1;
                 t1 = t2;
-                xb = enc_hist_tokens(m, t0, t1, S.freq);
+                xb = enc_hist_tokens(m, t0, t1, false);
             }
         }
-        enc_emit_block(S, k, m, t0, t1, xb, true);
+        enc_emit_block(&k, m, t0, t1, xb, true);
     }
     // pad to a byte boundary, Adler-32 big-endian
     const uint32_t adler = job.adler[c];
@@ -725,13 +761,12 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
 
 // Persistent warps pulling chunks from a global counter (same reason as inflate_kernel: no idle warps behind a long chunk).
 ZWZ_KERNEL __launch_bounds__(ZWZ_DE_WARPS * 32) deflate_encode_kernel(DeflateJob job, uint32_t *work_counter) {
-    __shared__ EncWarpSmem smem[ZWZ_DE_WARPS];
     for (;;) {
         uint32_t c = 0;
         if (lane_id() == 0) c = atomicAdd(work_counter, 1u);
         c = __shfl_sync(ZWZ_FULL, c, 0);
         if (c >= job.n) break;
-        enc_chunk(smem[warp_id()], job, c);
+        enc_chunk(enc_smem(), job, c);
         __syncwarp();
     }
 }

@@ -10,6 +10,7 @@
 
 #ifdef ZWZ_EMU
 #define ZWZ_DEV static inline
+#define ZWZ_DEV_NOINLINE static
 #define ZWZ_KERNEL static void
 #define ZWZ_DYN_SMEM(name) unsigned char *name = simt::dyn_smem()
 #define ZWZ_SPIN_PAUSE() zwz_emu_spin_pause()
@@ -17,6 +18,7 @@
 #else
 #include <cuda_runtime.h>
 #define ZWZ_DEV __device__ __forceinline__
+#define ZWZ_DEV_NOINLINE __device__ __noinline__
 #define ZWZ_KERNEL __global__ void
 #define ZWZ_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define ZWZ_SPIN_PAUSE() __nanosleep(20)

@@ -81,7 +81,7 @@ struct zwz_ctx {
     std::string err;
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
-    int inflate_mode = 0; // 0 = by batch size, 1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
+    int inflate_mode = 0; // 0/1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
@@ -445,7 +445,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         uint32_t grid2 = std::min<uint32_t>((job.n + ZWZ_DE_WARPS - 1) / ZWZ_DE_WARPS, (uint32_t) ctx->sm_count * 8u);
         {
             ProfSpan ps(ctx, ZWZ_PROF_ENCODE, st);
-            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, 0, st, job, d_counters + 4);
+            ZWZ_LAUNCH(zwz::deflate_encode_kernel, grid2, ZWZ_DE_WARPS * 32, ZWZ_DE_SMEM, st, job, d_counters + 4);
         }
         if ((rc = check_launch(ctx, "deflate_encode_kernel"))) return rc;
     }
@@ -595,10 +595,11 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
     if (!off || !len || !raw_off || !raw_len || !status) return fail(ctx, ZWZ_E_ARG, "null argument");
     zwz_rt::set_device(ctx->device);
     zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
-    // Mapping: one warp per stream (inflate.cuh) when the batch is small — a warp finishes one stream sooner than a lane
-    // does — and one lane per stream (inflate_lanes.cuh) when there are enough streams to fill the GPU that way. The lane
-    // kernel keeps its Adler-32 sums unreduced and its bit counts in 32 bits, hence the size limits.
-    bool lanes = ctx->inflate_mode == 2 || (ctx->inflate_mode == 0 && n >= (uint32_t) ctx->sm_count * 3u * 32u);
+    // Mapping: one warp per stream (inflate.cuh) is the product path. One lane per stream (inflate_lanes.cuh,
+    // ZWZ_INFLATE_MODE=lanes) needs ~40x fewer warp-instructions per byte but only three warps fit an SM next to its
+    // per-lane tables, and at that occupancy it runs latency-bound: 140 ms against 68 ms per C2 step on B200. It stays as a
+    // tested alternative mapping. It keeps its Adler-32 sums unreduced and its bit counts in 32 bits, hence the size limits.
+    bool lanes = ctx->inflate_mode == 2; // opt-in only: measured slower than the warp mapping on B200 (inflate)
     for (uint32_t i = 0; lanes && i < n; ++i)
         if (len[i] >= (1u << 28) || raw_off[i + 1] - raw_off[i] > (1ull << 24)) lanes = false;
     const size_t m_off = 0, m_roff = (size_t) n * 8, m_len = m_roff + (size_t) (n + 1) * 8, m_order = m_len + (size_t) n * 4,
