@@ -449,22 +449,33 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
                 if (litmask & 1u) {
                     uint32_t J = lane + (el & 15u);
                     uint32_t R = ok ? (1u << lane) : 0u;
-                    // a window of 32 bits holds at most 32 / min_ll code starts: 3 doubling rounds reach 8 of them, 4 reach 16
-                    const int rounds = min_ll >= 4u ? 3 : (min_ll >= 2u ? 4 : 5);
-                    for (int r = 0; r < rounds; ++r) {
-                        const bool go = ok && J < 32u && ((litmask >> J) & 1u);
-                        const int from = go ? (int) J : (int) lane;
-                        const uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);
-                        const uint32_t Jj = __shfl_sync(ZWZ_FULL, J, from);
-                        if (go) {
-                            R |= Rj;
-                            J = Jj;
+                    // a window of 32 bits holds at most ceil(32 / min_ll) code starts and r doubling rounds reach 2^r of them:
+                    // 2 rounds when no code is shorter than 8 bits (near-uniform bytes: the JPEG-like class), 3 down to 4 bits
+#define INF_ROUND()                                                                  \
+    do {                                                                             \
+        const bool go = ok && J < 32u && ((litmask >> J) & 1u);                      \
+        const int from = go ? (int) J : (int) lane;                                  \
+        const uint32_t Rj = __shfl_sync(ZWZ_FULL, R, from);                          \
+        const uint32_t Jj = __shfl_sync(ZWZ_FULL, J, from);                          \
+        if (go) {                                                                    \
+            R |= Rj;                                                                 \
+            J = Jj;                                                                  \
+        }                                                                            \
+    } while (0)
+                    INF_ROUND();
+                    INF_ROUND();
+                    if (min_ll < 8u) {
+                        INF_ROUND();
+                        if (min_ll < 4u) {
+                            INF_ROUND();
+                            if (min_ll < 2u) INF_ROUND();
                         }
                     }
+#undef INF_ROUND
                     const uint32_t R0 = __shfl_sync(ZWZ_FULL, R, 0);
                     const uint32_t J0 = __shfl_sync(ZWZ_FULL, J, 0);
                     const uint32_t nlit = (uint32_t) __popc(R0);
-                    INF_FLUSH_LITS();
+                    if (pend_lo != pos) INF_FLUSH_LITS(); // only after a step of the scalar path
                     if ((R0 >> lane) & 1u) {
                         const uint32_t q = pos + (uint32_t) __popc(R0 & ((1u << lane) - 1u));
                         if (q < cap) out[q] = (uint8_t) (el >> 16);
