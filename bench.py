@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="end-to-end leg: worker contexts (stream + buffers each)")
+    ap.add_argument("--e2e-parts", type=int, default=16, help="end-to-end leg: parts the shard is cut into")
     ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
                     help="auto: on for c2/c1 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
                          "the MD5 of ONE file is a single serial chain, one lane, ~0.1 GB/s)")
@@ -379,10 +381,10 @@ def main():
     # pinned host memory and ends in pinned host memory inside the timed region.
     import threading
     from concurrent.futures import ThreadPoolExecutor
-    W = 3
+    W = max(1, args.e2e_workers)
     first_chunk_of_file = np.concatenate([[0], np.cumsum(np.bincount(cfile, minlength=nf))]).astype(np.int64)
     if nf > 1:   # cut on file boundaries (MD5 needs whole files), parts of about equal bytes
-        want = min(16, max(1, nf // 2000))
+        want = min(args.e2e_parts, max(1, nf // 2000))
         part_file = np.unique(np.searchsorted(foffs, np.linspace(0, U, want + 1)))
         part_file[0], part_file[-1] = 0, nf
         part_file = np.unique(part_file)
@@ -392,7 +394,7 @@ def main():
         part_chunk = np.array([0, n], dtype=np.int64)
     else:
         part_file = None
-        part_chunk = np.unique(np.linspace(0, n, min(16, max(1, n // 512)) + 1).astype(np.int64))
+        part_chunk = np.unique(np.linspace(0, n, min(args.e2e_parts, max(1, n // 512)) + 1).astype(np.int64))
     nparts = len(part_chunk) - 1
     max_raw = max(int(raw_off[part_chunk[i + 1]] - raw_off[part_chunk[i]]) for i in range(nparts))
     max_slot = max(int(slot_off[part_chunk[i + 1]] - slot_off[part_chunk[i]]) for i in range(nparts))

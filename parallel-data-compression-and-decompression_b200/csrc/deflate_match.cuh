@@ -48,7 +48,8 @@ template <> struct MatchClass<1> {
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<2> {
-    static constexpr uint32_t kCap = 32768, kThreads = 512, kHBits = 13, kData = 32768 + 64, kListBits = 4;
+    // 31 744, not 32 768: 2 x (smem + 1 KB) must fit the SM's 228 KB for two resident CTAs (115 712 B each at most)
+    static constexpr uint32_t kCap = 31744, kThreads = 512, kHBits = 13, kData = 31744 + 64, kListBits = 4;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<3> {
@@ -66,6 +67,9 @@ struct MatchCtl {
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
 static_assert(sizeof(MatchCtl) <= 640, "MatchCtl must fit its slot");
+static_assert(2u * (MatchClass<2>::kSmem + 1024u) <= 228u * 1024u && 3u * (MatchClass<1>::kSmem + 1024u) <= 228u * 1024u &&
+                  6u * (MatchClass<0>::kSmem + 1024u) <= 228u * 1024u,
+              "resident CTAs per SM assumed by the launch grids");
 
 // scratch layout of one chunk (uint32 units): [0, A) best match per position, then tokens in place (deflate_encode.cuh);
 // [A, A + B) the hash-partitioned position lists (u16) used only inside lz_match_kernel

@@ -377,7 +377,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
         uint32_t b = sub_begin[s], e = sub_begin[s + 1];
         uint32_t *o = h_order + b;
         uint32_t k = 0;
-        static const uint32_t kClassHi[4] = {8192u, 16384u, 32768u, 65535u};
+        static const uint32_t kClassHi[4] = {zwz::MatchClass<0>::kCap, zwz::MatchClass<1>::kCap, zwz::MatchClass<2>::kCap, zwz::MatchClass<3>::kCap};
         for (int cls = 0; cls < 4; ++cls) {
             cls_begin[s * 5 + cls] = k;
             uint32_t lo_len = cls == 0 ? 0u : kClassHi[cls - 1] + 1u, hi_len = kClassHi[cls];

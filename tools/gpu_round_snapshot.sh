@@ -14,9 +14,10 @@ timeout 900 python bench.py --workload c1 --files 2147483648 --steps 3 > $O/benc
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > $O/plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1
-# warm-up = 3 steps; per step the kernels launch in the order match(S,M,L) encode md5 pack inflate md5 => skip the warm-up launches of each kernel
-ncu --set full --clock-control none --import-source on -k regex:lz_match -s 9 -c 3 -f -o $O/lz_match $CMD > $O/ncu_lz_match.log 2>&1
+# warm-up = 3 steps; per step the kernels launch in the order match(4 size classes) encode md5 pack inflate md5 => skip the warm-up launches of each kernel
+ncu --set full --clock-control none --import-source on -k regex:lz_match -s 12 -c 4 -f -o $O/lz_match $CMD > $O/ncu_lz_match.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:deflate_encode -s 3 -c 1 -f -o $O/deflate_encode $CMD > $O/ncu_deflate_encode.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:inflate -s 3 -c 1 -f -o $O/inflate $CMD > $O/ncu_inflate.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:md5_files -s 6 -c 1 -f -o $O/md5_files $CMD > $O/ncu_md5.log 2>&1
+timeout 600 python tools/cli_compare.py --mb 2000 --ranks 2 --tmp /dev/shm --out $O/cli_compare_2GB.json > $O/cli_compare.log 2>&1
 ls -la $O
