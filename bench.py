@@ -264,8 +264,8 @@ def main():
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=3, help="end-to-end leg: worker contexts (stream + buffers each)")
-    ap.add_argument("--e2e-parts", type=int, default=16, help="end-to-end leg: parts the shard is cut into")
+    ap.add_argument("--e2e-workers", type=int, default=6, help="end-to-end leg: worker contexts (stream + buffers each)")
+    ap.add_argument("--e2e-parts", type=int, default=32, help="end-to-end leg: parts the shard is cut into")
     ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
                     help="auto: on for c2/c1 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
                          "the MD5 of ONE file is a single serial chain, one lane, ~0.1 GB/s)")
@@ -548,7 +548,9 @@ def main():
         achieved = alg_bytes / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))   # measured on one workload only
+            if tj.get("workload") == args.workload and (args.files in (0, tj.get("files"))):
+                traffic = tj["kernels"].get(dom) * K / max(nl[dom], 1)   # per launch, like algorithmic_bytes_per_launch
         except Exception:
             pass
         line = {
