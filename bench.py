@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=6, help="end-to-end leg: worker contexts (stream + buffers each)")
+    ap.add_argument("--e2e-workers", type=int, default=0, help="end-to-end leg: worker contexts (stream + buffers each) per rank; 0 = min(6, host cores / ranks), at least 2")
     ap.add_argument("--e2e-parts", type=int, default=32, help="end-to-end leg: parts the shard is cut into")
     ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
                     help="auto: on for c2/c1 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
@@ -381,7 +381,7 @@ def main():
     # pinned host memory and ends in pinned host memory inside the timed region.
     import threading
     from concurrent.futures import ThreadPoolExecutor
-    W = max(1, args.e2e_workers)
+    W = args.e2e_workers if args.e2e_workers > 0 else max(2, min(6, (os.cpu_count() or 16) // max(world, 1)))
     first_chunk_of_file = np.concatenate([[0], np.cumsum(np.bincount(cfile, minlength=nf))]).astype(np.int64)
     if nf > 1:   # cut on file boundaries (MD5 needs whole files), parts of about equal bytes
         want = min(args.e2e_parts, max(1, nf // 2000))
