@@ -82,6 +82,7 @@ struct zwz_ctx {
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
     int inflate_mode = 0; // 0/1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
+    bool trace = false;   // ZWZ_TRACE=1: wall-clock phases of the host-buffer calls on stderr (syncs the stream at every mark)
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
     // optional per-kernel timing
@@ -113,12 +114,12 @@ int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
     if (a.cap >= bytes && a.p) return ZWZ_OK;
     if (a.p) {
         zwz_rt::stream_sync(ctx->stream);
-        if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_device(a.p);
+        if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_arena(a.p, ctx->stream);
         a.p = nullptr;
         a.cap = 0;
     }
-    size_t want = bytes + bytes / 8 + 4096; // grow-only, with headroom
-    int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : zwz_rt::malloc_device(&a.p, want);
+    size_t want = bytes + bytes / 4 + 4096; // grow-only, with headroom: batches of one job differ by a few percent
+    int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : zwz_rt::malloc_arena(&a.p, want, ctx->stream);
     if (rc) {
         a.p = nullptr;
         return fail(ctx, ZWZ_E_NOMEM, pinned ? "pinned allocation failed" : "device allocation failed");
@@ -128,9 +129,9 @@ int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
     return ZWZ_OK;
 }
 
-void release(Arena &a) {
+void release(zwz_ctx *ctx, Arena &a) {
     if (!a.p) return;
-    if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_device(a.p);
+    if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_arena(a.p, ctx->stream);
     a.p = nullptr;
     a.cap = 0;
 }
@@ -164,6 +165,32 @@ int check_launch(zwz_ctx *ctx, const char *what) {
     }
     return ZWZ_OK;
 }
+
+// ZWZ_TRACE=1: phase times of a host-buffer call (debugging aid: every mark synchronises the stream)
+struct Trace {
+    zwz_ctx *ctx;
+    const char *call;
+    double t0;
+    std::string line;
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+    }
+    Trace(zwz_ctx *c, const char *name) : ctx(c), call(name), t0(c->trace ? now() : 0.0) {}
+    void mark(const char *what) {
+        if (!ctx->trace) return;
+        zwz_rt::stream_sync(ctx->stream);
+        double t = now();
+        char buf[64];
+        snprintf(buf, sizeof buf, " %s %.2f ms,", what, (t - t0) * 1e3);
+        line += buf;
+        t0 = t;
+    }
+    ~Trace() {
+        if (ctx->trace && !line.empty()) fprintf(stderr, "[zwz trace %p] %s:%s\n", (void *) ctx, call, line.c_str());
+    }
+};
 
 struct LevelParams {
     uint32_t depth, nice;
@@ -211,6 +238,8 @@ int zwz_init(int device, zwz_ctx **out) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
+    zwz_rt::keep_pool_memory(device);
+    if (const char *e = getenv("ZWZ_TRACE")) ctx->trace = *e && *e != '0';
     if (const char *e = getenv("ZWZ_INFLATE_MODE")) ctx->inflate_mode = !strcmp(e, "warp") ? 1 : (!strcmp(e, "lanes") ? 2 : 0);
     if (const char *e = getenv("ZWZ_BATCH_RAW_MB")) {
         long v = atol(e);
@@ -224,14 +253,15 @@ void zwz_destroy(zwz_ctx *ctx) {
     if (!ctx) return;
     zwz_rt::set_device(ctx->device);
     zwz_rt::stream_sync(ctx->stream);
-    release(ctx->meta);
-    release(ctx->scratch);
-    release(ctx->bulk_in);
-    release(ctx->bulk_out);
-    release(ctx->packed);
-    release(ctx->pin_meta);
-    release(ctx->pin_aux);
-    release(ctx->counter);
+    release(ctx, ctx->meta);
+    release(ctx, ctx->scratch);
+    release(ctx, ctx->bulk_in);
+    release(ctx, ctx->bulk_out);
+    release(ctx, ctx->packed);
+    release(ctx, ctx->pin_meta);
+    release(ctx, ctx->pin_aux);
+    release(ctx, ctx->counter);
+    zwz_rt::stream_sync(ctx->stream);
     zwz_rt::stream_destroy(ctx->stream);
     delete ctx;
 }
@@ -706,9 +736,12 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
         slot[i + 1] = slot[i] + (((uint64_t) rec_cap[i] + 15u) & ~15ull);
     }
     int rc;
+    Trace tr(ctx, "decompress_records");
     if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
     if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
+    tr.mark("reserve");
     if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, comp + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "compressed upload failed");
+    tr.mark("h2d");
     // per-record capacity is rec_cap, but slots are 16-byte aligned so the gather can use 128-bit copies
     std::vector<uint64_t> cap_off(n + 1);
     for (uint32_t i = 0; i <= n; ++i) cap_off[i] = slot[i];
@@ -717,6 +750,7 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     if ((rc = zwz_inflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, coff.data(), len, n, (uint8_t *) ctx->bulk_out.p, cap_off.data(),
                                        raw_len, status, flags, nullptr)))
         return rc;
+    tr.mark("inflate");
     bool retry = false;
     for (uint32_t i = 0; i < n; ++i) {
         if (status[i] == ZWZ_STREAM_OUTPUT_FULL || raw_len[i] > rec_cap[i]) {
@@ -743,6 +777,7 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     // NOT pin_meta: md5_launch below refills pin_meta while this upload may still be in flight (page-locked memory is read by
     // the DMA engine after cudaMemcpyAsync returns) — a reuse race that corrupted gather descriptors once per ~10^5 records.
     if ((rc = reserve(ctx, ctx->pin_aux, meta_bytes, true))) return rc;
+    tr.mark("reserve2");
     uint8_t *hp = (uint8_t *) ctx->pin_aux.p;
     memcpy(hp, slot.data(), (size_t) n * 8);
     memcpy(hp + m_dst, dst.data(), (size_t) n * 8);
@@ -756,6 +791,7 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
                    (const uint64_t *) (dmeta + m_dst), (const uint32_t *) (dmeta + m_len), d_files, n);
     }
     if ((rc = check_launch(ctx, "gather_records_kernel"))) return rc;
+    tr.mark("gather");
     if (digest && nf) {
         std::vector<uint64_t> fo(nf), fl(nf);
         for (uint32_t i = 0; i < nf; ++i) {
@@ -764,8 +800,10 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
         }
         if ((rc = md5_launch(ctx, nullptr, d_files, fo.data(), fl.data(), nullptr, nf, digest, 1, nullptr))) return rc;
     }
+    tr.mark("md5");
     if (zwz_rt::memcpy_d2h(files_out, d_files, (size_t) acc, ctx->stream) || zwz_rt::stream_sync(ctx->stream))
         return fail(ctx, ZWZ_E_CUDA, "raw download failed");
+    tr.mark("d2h");
     return ZWZ_OK;
 }
 

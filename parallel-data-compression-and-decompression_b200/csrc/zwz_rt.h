@@ -31,6 +31,9 @@ inline int malloc_device(void **p, size_t n) {
     return *p ? 0 : 2;
 }
 inline int free_device(void *p) { free(p); return 0; }
+inline int malloc_arena(void **p, size_t n, zwz_stream_t) { return malloc_device(p, n); }
+inline int free_arena(void *p, zwz_stream_t) { return free_device(p); }
+inline int keep_pool_memory(int) { return 0; }
 inline int malloc_pinned(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 inline int free_pinned(void *p) { free(p); return 0; }
 inline int stream_create(zwz_stream_t *s) { *s = nullptr; return 0; }
@@ -77,6 +80,19 @@ inline int device_props(int d, int *sms, int *maj, int *min, size_t *mem, size_t
 }
 inline int malloc_device(void **p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : 2; }
 inline int free_device(void *p) { return cudaFree(p) == cudaSuccess ? 0 : 1; }
+// Arenas come from the stream-ordered allocator: cudaMalloc/cudaFree synchronise the whole device, which stalls every other
+// context of the process (the host's worker pool saw ~0.7 s stalls behind another worker's long MD5 kernel).
+inline int malloc_arena(void **p, size_t n, zwz_stream_t st) {
+    if (cudaMallocAsync(p, n ? n : 1, st) != cudaSuccess) return 2;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 2; // usable from any stream afterwards
+}
+inline int free_arena(void *p, zwz_stream_t st) { return cudaFreeAsync(p, st) == cudaSuccess ? 0 : 1; }
+inline int keep_pool_memory(int device) { // freed arena memory stays in the pool instead of going back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return 1;
+    unsigned long long keep = ~0ull;
+    return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess ? 0 : 1;
+}
 inline int malloc_pinned(void **p, size_t n) { return cudaMallocHost(p, n ? n : 1) == cudaSuccess ? 0 : 2; }
 inline int free_pinned(void *p) { return cudaFreeHost(p) == cudaSuccess ? 0 : 1; }
 inline int stream_create(zwz_stream_t *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1; }

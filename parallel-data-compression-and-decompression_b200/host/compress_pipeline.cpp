@@ -10,6 +10,7 @@
 // NUM_CONSUMERS = 1.
 #include "pipeline.hpp"
 
+#include <algorithm>
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
@@ -111,14 +112,19 @@ struct Job {
     const std::vector<PlannedFile> &files;
     const std::vector<Batch> &batches;
     int fd;
-    size_t cap; // staging capacity of a worker
+    size_t cap;     // staging capacity of a worker
+    size_t out_cap; // enough for the packed streams of any planned batch: page-locked buffers are sized once per worker
     int level;
     int device;
     std::atomic<size_t> next_batch{0};
     OrderedCommit order;
     uint64_t archive_off = 0; // guarded by the commit order
     Job(const std::string &in, const std::vector<PlannedFile> &f, const std::vector<Batch> &b, int fd_, size_t cap_, int level_, int device_)
-        : input_dir(in), files(f), batches(b), fd(fd_), cap(cap_), level(level_), device(device_) {}
+        : input_dir(in), files(f), batches(b), fd(fd_), cap(cap_), out_cap(0), level(level_), device(device_) {
+        size_t max_files = 1;
+        for (const auto &x : b) max_files = std::max(max_files, x.count);
+        out_cap = cap + (cap / CHUNK_SIZE + max_files + 16) * 64 + 4096;
+    }
 };
 
 class Worker {
@@ -171,7 +177,7 @@ class Worker {
             std::vector<uint64_t> poff(nc + 1);
             std::vector<zwz_deflate_result> res(nc);
             std::vector<uint8_t> digest((size_t) nf * 16);
-            out_.reserve(used + nc * 64 + 4096);
+            out_.reserve(std::max<size_t>(job_.out_cap, used + nc * 64 + 4096));
             t0 = now_seconds();
             int rc = zwz_compress_files(ctx_, stage_.data(), foff.data(), nf, job_.level, out_.data(), out_.cap, poff.data(), res.data(),
                                         digest.data());
@@ -315,6 +321,15 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
     }
     std::cout << "Max record line num: " << count_non_empty_lines(file_record) << std::endl;
 
+    // the device comes up while the files are dealt and sized
+    std::exception_ptr warm_error;
+    std::thread warm([&] {
+        try {
+            ctx_for(cfg.device);
+        } catch (...) {
+            warm_error = std::current_exception();
+        }
+    });
     // the deal, then the plan: whole files per batch, in deal order
     std::vector<PlannedFile> files;
     int file_number = 0, next_file_number = world_rank;
@@ -341,6 +356,11 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         batches.back().bytes += files[i].size;
     }
 
+    warm.join();
+    if (warm_error) {
+        ::close(fd);
+        std::rethrow_exception(warm_error);
+    }
     Job job(input_dir, files, batches, fd, cap, cfg.level, cfg.device);
     const int workers = (int) std::min<size_t>((size_t) worker_count(), std::max<size_t>(1, batches.size()));
     try {

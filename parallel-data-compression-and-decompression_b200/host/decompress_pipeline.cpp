@@ -195,10 +195,20 @@ struct Job {
     const std::string &output_dir;
     uint64_t budget;
     int device;
+    size_t max_comp = 0, max_out = 0; // of any planned group: page-locked buffers are sized once per worker
     std::atomic<size_t> next_group{0};
     OrderedCommit order;
     Job(std::vector<Archive> &a, const std::vector<Group> &g, const std::string &out, uint64_t budget_, int device_)
-        : archives(a), groups(g), output_dir(out), budget(budget_), device(device_) {}
+        : archives(a), groups(g), output_dir(out), budget(budget_), device(device_) {
+        for (const auto &x : g) {
+            if (x.big) continue;
+            size_t comp = 0;
+            for (size_t f = x.first; f < x.first + x.count; ++f)
+                for (const auto &r : a[x.archive].files[f].ordered) comp += r.len;
+            max_comp = std::max(max_comp, comp);
+            max_out = std::max(max_out, x.nrec * CHUNK_SIZE);
+        }
+    }
 };
 
 class Worker {
@@ -267,7 +277,8 @@ class Worker {
         uint64_t comp_bytes = 0;
         for (size_t f = grp.first; f < grp.first + grp.count; ++f)
             for (const auto &r : a.files[f].ordered) comp_bytes += r.len;
-        in_.reserve(comp_bytes + 64);
+        in_.reserve(std::max<size_t>(comp_bytes, job_.max_comp) + 64);
+        out_.reserve(job_.max_out + 64);
         std::vector<uint64_t> off, foff(nf + 1);
         std::vector<uint32_t> len, rfile;
         off.reserve(grp.nrec);
@@ -388,6 +399,16 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
     }
     std::sort(names.begin(), names.end());
 
+    // the device comes up (CUDA runtime + first context: 0.5–2.5 s depending on how many GPUs are visible) while the archives
+    // are mapped and indexed
+    std::exception_ptr warm_error;
+    std::thread warm([&] {
+        try {
+            if (!names.empty()) ctx_for(cfg.device);
+        } catch (...) {
+            warm_error = std::current_exception();
+        }
+    });
     double t0 = now_seconds();
     std::vector<Archive> archives;
     archives.reserve(names.size());
@@ -426,6 +447,8 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
         }
     }
     stats().t_read += now_seconds() - t0;
+    warm.join();
+    if (warm_error) std::rethrow_exception(warm_error);
 
     Job job(archives, groups, output_dir, budget, cfg.device);
     const int workers = (int) std::min<size_t>((size_t) worker_count(), std::max<size_t>(1, groups.size()));

@@ -55,6 +55,25 @@ void print_timing(const char *what) {
     }
 }
 
+// GPUs this process may use, without initialising CUDA: the entries of CUDA_VISIBLE_DEVICES if set, else the /dev/nvidia<N>
+// nodes; the CUDA runtime is asked only if neither says anything.
+int visible_gpu_count() {
+    if (const char *v = std::getenv("CUDA_VISIBLE_DEVICES")) {
+        if (!*v) return 0;
+        int n = 1;
+        for (const char *p = v; *p; ++p) n += *p == ',';
+        return n;
+    }
+    int n = 0;
+    std::error_code ec;
+    for (const auto &e : fs::directory_iterator("/dev", ec)) {
+        const std::string name = e.path().filename().string();
+        if (name.size() > 6 && name.compare(0, 6, "nvidia") == 0 && std::all_of(name.begin() + 6, name.end(), [](unsigned char ch) { return std::isdigit(ch) != 0; }))
+            ++n;
+    }
+    return n > 0 ? n : zwz_device_count();
+}
+
 static int env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
@@ -67,8 +86,11 @@ void config_from_env() {
     RunConfig &c = config();
     c.world_rank = env_int("ZWZ_RANK", env_int("OMPI_COMM_WORLD_RANK", env_int("PMI_RANK", env_int("RANK", 0))));
     c.world_size = env_int("ZWZ_WORLD", env_int("OMPI_COMM_WORLD_SIZE", env_int("PMI_SIZE", env_int("WORLD_SIZE", 1))));
-    int ndev = zwz_device_count();
     int local = env_int("ZWZ_LOCAL_RANK", env_int("OMPI_COMM_WORLD_LOCAL_RANK", env_int("LOCAL_RANK", c.world_rank)));
+    // Local rank 0 needs no device count (device 0), and the count is taken without touching CUDA where possible: the runtime
+    // then initialises on a helper thread while the host walks directories / indexes archives, and ZWZ_GPUS can fork before any
+    // CUDA call has been made.
+    int ndev = local > 0 ? visible_gpu_count() : 1;
     c.device = env_int("ZWZ_DEVICE", ndev > 0 ? local % ndev : 0);
     c.level = env_int("ZWZ_LEVEL", 0);
     c.verbose = env_int("ZWZ_VERBOSE", 0) != 0;

@@ -78,7 +78,7 @@ int main(int argc, char *argv[]) {
     double start_time = now_s();
     config_from_env();
     RunConfig &cfg = config();
-    timing_mark("configured (CUDA runtime initialised)");
+    timing_mark("configured");
 
     if (argc < 4) { // main.cpp:88-92
         std::cerr << "Usage: " << argv[0] << " <compress/decompress> <source directory path> <output directory path>\n";
@@ -118,7 +118,7 @@ int main(int argc, char *argv[]) {
             pid_t pid = fork(); // before any CUDA call in this process
             if (pid == 0) {
                 cfg.world_rank = r;
-                int ndev = zwz_device_count();
+                int ndev = visible_gpu_count();
                 cfg.device = ndev > 0 ? r % ndev : 0;
                 kids.clear();
                 break;

@@ -20,7 +20,9 @@ zwz_ctx *ctx_for(int device) {
     if (it != all.end()) return it->second;
     zwz_ctx *c = nullptr;
     double t0 = now_seconds();
-    int rc = zwz_init(device, &c);
+    // the rank's device index was derived without asking CUDA (distribute.cpp); fold it into what the runtime really offers
+    const int nd = zwz_device_count();
+    int rc = zwz_init(nd > 0 ? device % nd : device, &c);
     stats().t_init += now_seconds() - t0;
     if (rc != ZWZ_OK || !c) {
         std::cerr << "zwz: cannot initialise CUDA device " << device << " (error " << rc << "); there is no CPU fallback" << std::endl;
@@ -42,7 +44,8 @@ zwz_ctx *worker_ctx(int device, int worker) {
     auto it = all.find(key);
     if (it != all.end()) return it->second;
     zwz_ctx *c = nullptr;
-    if (zwz_init(device, &c) != ZWZ_OK || !c) throw std::runtime_error("zwz_init failed for a worker context");
+    const int nd = zwz_device_count();
+    if (zwz_init(nd > 0 ? device % nd : device, &c) != ZWZ_OK || !c) throw std::runtime_error("zwz_init failed for a worker context");
     if (timing_level() >= 2) zwz_profile_enable(c, 1);
     all[key] = c;
     return c;

@@ -41,6 +41,7 @@ struct RunConfig {
 };
 RunConfig &config();
 void config_from_env();
+int visible_gpu_count(); // without initialising CUDA when possible
 
 // deterministic walk + size-descending sort, shared by sort_files_by_size and by ranks that recompute the deal
 std::vector<FileEntry> collect_and_sort(const std::filesystem::path &path);
