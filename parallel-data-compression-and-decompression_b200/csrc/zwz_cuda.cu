@@ -82,6 +82,7 @@ struct zwz_ctx {
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
     int inflate_mode = 0; // 0/1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
+    bool arena_async = true; // ZWZ_ARENA_SYNC=1: plain cudaMalloc/cudaFree arenas (for A/B timing)
     bool trace = false;   // ZWZ_TRACE=1: wall-clock phases of the host-buffer calls on stderr (syncs the stream at every mark)
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
     size_t last_res_off = 0, last_slot_off = 0; // where the last deflate call left results / slot offsets inside `meta`
@@ -114,12 +115,12 @@ int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
     if (a.cap >= bytes && a.p) return ZWZ_OK;
     if (a.p) {
         zwz_rt::stream_sync(ctx->stream);
-        if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_arena(a.p, ctx->stream);
+        if (a.pinned) zwz_rt::free_pinned(a.p); else if (ctx->arena_async) zwz_rt::free_arena(a.p, ctx->stream); else zwz_rt::free_device(a.p);
         a.p = nullptr;
         a.cap = 0;
     }
     size_t want = bytes + bytes / 4 + 4096; // grow-only, with headroom: batches of one job differ by a few percent
-    int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : zwz_rt::malloc_arena(&a.p, want, ctx->stream);
+    int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : (ctx->arena_async ? zwz_rt::malloc_arena(&a.p, want, ctx->stream) : zwz_rt::malloc_device(&a.p, want));
     if (rc) {
         a.p = nullptr;
         return fail(ctx, ZWZ_E_NOMEM, pinned ? "pinned allocation failed" : "device allocation failed");
@@ -131,7 +132,7 @@ int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
 
 void release(zwz_ctx *ctx, Arena &a) {
     if (!a.p) return;
-    if (a.pinned) zwz_rt::free_pinned(a.p); else zwz_rt::free_arena(a.p, ctx->stream);
+    if (a.pinned) zwz_rt::free_pinned(a.p); else if (ctx->arena_async) zwz_rt::free_arena(a.p, ctx->stream); else zwz_rt::free_device(a.p);
     a.p = nullptr;
     a.cap = 0;
 }
@@ -239,6 +240,13 @@ int zwz_init(int device, zwz_ctx **out) {
         return ZWZ_E_NODEVICE;
     }
     zwz_rt::keep_pool_memory(device);
+    zwz_rt::preload_kernel((const void *) zwz::deflate_encode_kernel);
+    zwz_rt::preload_kernel((const void *) zwz::inflate_kernel);
+    zwz_rt::preload_kernel((const void *) zwz::md5_files_kernel);
+    zwz_rt::preload_kernel((const void *) zwz::pack_streams_kernel);
+    zwz_rt::preload_kernel((const void *) zwz::gather_records_kernel);
+    zwz_rt::preload_kernel((const void *) zwz::adler32_kernel);
+    if (const char *e = getenv("ZWZ_ARENA_SYNC")) ctx->arena_async = !(*e && *e != '0');
     if (const char *e = getenv("ZWZ_TRACE")) ctx->trace = *e && *e != '0';
     if (const char *e = getenv("ZWZ_INFLATE_MODE")) ctx->inflate_mode = !strcmp(e, "warp") ? 1 : (!strcmp(e, "lanes") ? 2 : 0);
     if (const char *e = getenv("ZWZ_BATCH_RAW_MB")) {
@@ -514,9 +522,12 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
         slot[i + 1] = slot[i] + zwz_deflate_bound(len[i]);
     }
     int rc;
+    Trace tr(ctx, "compress");
     if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
     if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
+    tr.mark("reserve");
     if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, raw + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "raw upload failed");
+    tr.mark("h2d");
     if (digest && md5_n) { // MD5 of the source files from the same resident copy (no second upload)
         std::vector<uint64_t> mo(md5_n);
         for (uint32_t i = 0; i < md5_n; ++i) mo[i] = md5_off[i] - lo;
@@ -525,12 +536,14 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
     if ((rc = zwz_deflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, roff.data(), len, n, (uint8_t *) ctx->bulk_out.p, slot.data(), res,
                                        level, nullptr)))
         return rc;
+    tr.mark("md5+deflate");
     for (uint32_t i = 0; i < n; ++i) packed_off[i + 1] = packed_off[i] + res[i].len0 + res[i].len1;
     if (packed_off[n] > out_cap) return fail(ctx, ZWZ_E_CAPACITY, "output buffer too small");
     // gather on the device so only the compressed bytes cross the bus
     const size_t pm = (size_t) (n + 1) * 8;
     if ((rc = reserve(ctx, ctx->packed, (size_t) packed_off[n] + align_up(pm, 256) + 256, false))) return rc;
     if ((rc = reserve(ctx, ctx->pin_meta, pm, true))) return rc;
+    tr.mark("reserve2");
     memcpy(ctx->pin_meta.p, packed_off, pm);
     uint8_t *d_poff = (uint8_t *) ctx->packed.p;
     uint8_t *d_packed = d_poff + align_up(pm, 256);
@@ -545,6 +558,7 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
                    (const uint64_t *) d_poff, n);
     }
     if ((rc = check_launch(ctx, "pack_streams_kernel"))) return rc;
+    tr.mark("pack");
     if (zwz_rt::memcpy_d2h(out, d_packed, (size_t) packed_off[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
         return fail(ctx, ZWZ_E_CUDA, "compressed download failed");
     return ZWZ_OK;

@@ -34,6 +34,7 @@ inline int free_device(void *p) { free(p); return 0; }
 inline int malloc_arena(void **p, size_t n, zwz_stream_t) { return malloc_device(p, n); }
 inline int free_arena(void *p, zwz_stream_t) { return free_device(p); }
 inline int keep_pool_memory(int) { return 0; }
+inline int preload_kernel(const void *) { return 0; }
 inline int malloc_pinned(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 inline int free_pinned(void *p) { free(p); return 0; }
 inline int stream_create(zwz_stream_t *s) { *s = nullptr; return 0; }
@@ -92,6 +93,12 @@ inline int keep_pool_memory(int device) { // freed arena memory stays in the poo
     if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return 1;
     unsigned long long keep = ~0ull;
     return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess ? 0 : 1;
+}
+// with lazy module loading (the CUDA 12 default) a kernel's code is loaded at its first launch, under a process-wide lock:
+// loading at init moves that cost to where the host overlaps it with its own planning
+inline int preload_kernel(const void *fn) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, fn) == cudaSuccess ? 0 : 1;
 }
 inline int malloc_pinned(void **p, size_t n) { return cudaMallocHost(p, n ? n : 1) == cudaSuccess ? 0 : 2; }
 inline int free_pinned(void *p) { return cudaFreeHost(p) == cudaSuccess ? 0 : 1; }
