@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--ranks", type=int, default=2)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "cli_compare.json"))
     ap.add_argument("--tmp", default=None)
+    ap.add_argument("--shape", default="c1", choices=["c1", "c2"], help="c1: 1000 mixed files up to 16 MiB; c2: image-like files of ~6.7 KB, 1000 per directory")
     a = ap.parse_args()
     tmp = tempfile.mkdtemp(prefix="zwz_cli_", dir=a.tmp)
     res = {"config": f"C1-shaped tree, ~{a.mb} MB, mixed T/S/I/R, sizes log-uniform 4 KiB..16 MiB", "ranks": a.ranks, "cores": os.cpu_count()}
@@ -71,12 +72,15 @@ def main():
         src = os.path.join(tmp, "w", "src")
         os.makedirs(src)
         specs, tot = [], 0
-        for s in corpus.c1_specs(1000, corpus.BASE_SEED):
+        pool = corpus.c1_specs(1000, corpus.BASE_SEED) if a.shape == "c1" else corpus.c2_specs(370_000, corpus.BASE_SEED)
+        for s in pool:
             if tot >= a.mb * 1e6:
                 break
             specs.append(s)
             tot += s.size
         corpus.write_tree(src, specs)
+        if a.shape == "c2":
+            res["config"] = f"C2-shaped tree, ~{a.mb} MB of image-like files (median 5.5 KiB), 1000 per directory"
         res["files"], res["bytes"] = len(specs), tot
 
         # ---- reference on the CPU: P emulated ranks, then 1-process decompress
