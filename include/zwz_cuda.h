@@ -8,9 +8,10 @@
  *   zwz_md5_batch*       replaces  verification.cpp:13-27    MD5_Init / MD5_Update* / MD5_Final per file (+ hex at :24-27)
  *
  * Every entry point is plain C: POD arguments, caller owns every buffer it passes, the library owns its device arenas,
- * return value 0 = ok / negative = ZWZ_E_*; nothing throws across the boundary. One zwz_ctx per GPU; a ctx may be
- * driven by one host thread at a time, different ctxs concurrently. There is NO CPU fallback: zwz_init fails when no
- * CUDA device is usable.
+ * return value 0 = ok / negative = ZWZ_E_*; nothing throws across the boundary. A zwz_ctx is one stream plus its device
+ * and page-locked arenas on one GPU; a ctx may be driven by one host thread at a time, different ctxs — on the same GPU
+ * or not — concurrently (the host keeps one per worker). There is NO CPU fallback: zwz_init fails when no CUDA device
+ * is usable.
  *
  * Two flavours of each batch call:
  *   *_device : bulk buffers are DEVICE pointers (inputs already resident in HBM); chunk descriptors (offset/length
