@@ -172,6 +172,10 @@ void print_verdict(Console &con, RunStats &st, const std::string &file_path, con
     }
 }
 
+const char *status_name(uint32_t s) {
+    return s == ZWZ_STREAM_TRUNCATED ? "truncated stream" : (s == ZWZ_STREAM_BAD ? "invalid stream or checksum" : (s == ZWZ_STREAM_OUTPUT_FULL ? "output larger than expected" : "ok"));
+}
+
 std::mutex &stats_mu() {
     static std::mutex mu;
     return mu;
@@ -184,6 +188,7 @@ void merge_stats(const RunStats &s) {
     g.raw_bytes += s.raw_bytes;
     g.md5_match += s.md5_match;
     g.md5_mismatch += s.md5_mismatch;
+    g.bad_records += s.bad_records;
     g.t_read += s.t_read;
     g.t_gpu += s.t_gpu;
     g.t_write += s.t_write;
@@ -236,12 +241,33 @@ class Worker {
     }
 
   private:
+    // Records whose stream did not reach a clean end (truncated, invalid, checksum mismatch). Counted always; named on stderr
+    // only with ZWZ_STRICT=1 — the reference writes whatever inflate produced and says nothing (decompression.cpp:31).
+    void report_bad_records(const Archive &a, size_t first_file, const std::vector<uint32_t> &rfile, const std::vector<uint32_t> &status,
+                            Console &con, RunStats &st) {
+        size_t k = 0;
+        uint32_t cur = 0xffffffffu;
+        for (size_t i = 0; i < status.size(); ++i) {
+            if (rfile[i] != cur) {
+                cur = rfile[i];
+                k = 0;
+            }
+            if (status[i] != ZWZ_STREAM_END) {
+                st.bad_records++;
+                const FileState &f = a.files[first_file + cur];
+                if (config().strict) con.err << "Corrupt record: " << f.relpath << " sequence " << f.ordered[k].seq << " (" << status_name(status[i]) << ")\n";
+            }
+            ++k;
+        }
+    }
+
     // inflate `nrec` records (payloads already compacted in in_) into out_, retrying with larger capacities for foreign
     // records that inflate to more than 65 535 bytes (the reference's loop handles any size, decompression.cpp:17-33)
     void inflate_group(std::vector<uint64_t> &off, std::vector<uint32_t> &len, std::vector<uint32_t> &rfile, uint32_t nf,
-                       std::vector<uint64_t> &foff, uint8_t *digest) {
+                       std::vector<uint64_t> &foff, uint8_t *digest, std::vector<uint32_t> &status) {
         const size_t nrec = off.size();
-        std::vector<uint32_t> cap(nrec, (uint32_t) CHUNK_SIZE), raw_len(nrec), status(nrec);
+        std::vector<uint32_t> cap(nrec, (uint32_t) CHUNK_SIZE), raw_len(nrec);
+        status.assign(nrec, 0u);
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
@@ -292,8 +318,11 @@ class Worker {
         st.t_read += now_seconds() - t0;
         std::vector<uint8_t> digest((size_t) nf * 16);
         t0 = now_seconds();
-        if (!off.empty())
-            inflate_group(off, len, rfile, nf, foff, digest.data());
+        std::vector<uint32_t> status;
+        if (!off.empty()) {
+            inflate_group(off, len, rfile, nf, foff, digest.data(), status);
+            report_bad_records(a, grp.first, rfile, status, con, st);
+        }
         else if (nf) // files without a single usable record: still created, and their verdict is that of the empty file
             zwz_md5_batch(ctx_, in_.data(), foff.data(), foff.data(), nf, digest.data());
         st.t_gpu += now_seconds() - t0;
@@ -347,7 +376,13 @@ class Worker {
             std::vector<uint32_t> len, rfile(r1 - r0, 0u);
             uint64_t used = 0;
             stage_payloads(a.bytes, fsx.ordered, r0, r1, used, off, len);
-            inflate_group(off, len, rfile, 1, foff, nullptr);
+            std::vector<uint32_t> status;
+            inflate_group(off, len, rfile, 1, foff, nullptr, status);
+            for (size_t i = 0; i < status.size(); ++i)
+                if (status[i] != ZWZ_STREAM_END) {
+                    st.bad_records++;
+                    if (config().strict) con.err << "Corrupt record: " << fsx.relpath << " sequence " << fsx.ordered[r0 + i].seq << " (" << status_name(status[i]) << ")\n";
+                }
             if (foff[1]) std::fwrite(out_.data(), 1, (size_t) foff[1], o);
             written += foff[1];
         }

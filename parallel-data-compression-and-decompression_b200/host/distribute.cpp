@@ -95,6 +95,7 @@ void config_from_env() {
     c.level = env_int("ZWZ_LEVEL", 0);
     c.verbose = env_int("ZWZ_VERBOSE", 0) != 0;
     c.verify_all = env_int("ZWZ_VERIFY_ALL", 0) != 0;
+    c.strict = env_int("ZWZ_STRICT", 0) != 0;
     int mb = env_int("ZWZ_BATCH_MB", 0);
     if (mb > 0) c.batch_bytes = (std::size_t) mb << 20;
 }

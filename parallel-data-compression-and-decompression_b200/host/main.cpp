@@ -142,6 +142,10 @@ int main(int argc, char *argv[]) {
         rc = 2;
     }
     timing_mark("operation finished");
+    if (cfg.strict && stats().bad_records != 0 && rc == 0) {
+        std::cerr << "ZWZ_STRICT: " << stats().bad_records << " record(s) did not decode cleanly" << std::endl;
+        rc = 4;
+    }
     if (self_gpus > 1 && cfg.world_rank != 0) _exit(rc);
     for (pid_t k : kids) {
         int st = 0;

@@ -37,6 +37,8 @@ struct RunConfig {
     int level = 0;            // 0 = library default
     bool verbose = false;     // per-file lines like the reference prints (compression.cpp:100, decompression.cpp:90,145)
     bool verify_all = false;  // also print an MD5 verdict for files whose last record arrived out of order
+    bool strict = false;      // ZWZ_STRICT=1: name every record that did not decode to a clean end of stream, exit code 4
+                              // (the reference ignores zlib's return codes, decompression.cpp:31 — and so does the default)
     std::size_t batch_bytes = (std::size_t) 128 << 20; // per worker (ZWZ_BATCH_MB)
 };
 RunConfig &config();
@@ -47,7 +49,7 @@ int visible_gpu_count(); // without initialising CUDA when possible
 std::vector<FileEntry> collect_and_sort(const std::filesystem::path &path);
 
 struct RunStats {
-    uint64_t files = 0, records = 0, raw_bytes = 0, payload_bytes = 0, md5_match = 0, md5_mismatch = 0;
+    uint64_t files = 0, records = 0, raw_bytes = 0, payload_bytes = 0, md5_match = 0, md5_mismatch = 0, bad_records = 0;
     double t_read = 0, t_gpu = 0, t_write = 0, t_init = 0; // seconds, printed with ZWZ_TIMING=1
 };
 double now_seconds();

@@ -139,6 +139,24 @@ def test_we_decompress_golden_archives(main_bin, name, tmp_path):
     assert log.count("MD5 mismatch for file") == man[name]["verdicts"]["mismatch"]
 
 
+def test_strict_mode_names_the_records_zlib_would_have_rejected(main_bin, tmp_path):
+    """ZWZ_STRICT=1: the reference ignores zlib's return codes (decompression.cpp:31); with the flag
+    every record that does not reach a clean end of stream is named and the exit code is 4. Same bytes are written either way.
+    The golden 1-rank archive holds the reference's own truncated records (incompressible 65 535-byte chunks, §5.1)."""
+    import oracle_lib as O
+    recs = zwz_format.parse(open(os.path.join(GOLD, "edge_r1", "compressed_0.zwz"), "rb").read())
+    bad = [(r.path, r.seq) for r in recs if O.inflate(r.payload, 70000)[1] != O.STREAM_END]
+    assert bad, "fixture lost its truncated records"
+    out1, out2 = str(tmp_path / "o1"), str(tmp_path / "o2")
+    r = subprocess.run([main_bin, "decompress", os.path.join(GOLD, "edge_r1"), out1], env={**os.environ, "ZWZ_STRICT": "1"}, capture_output=True, text=True)
+    assert r.returncode == 4, r.stderr[-2000:]
+    named = [l for l in r.stderr.splitlines() if l.startswith("Corrupt record: ")]
+    assert sorted(named) == sorted(f"Corrupt record: {p} sequence {q} (truncated stream)" for p, q in bad)
+    log = run([main_bin, "decompress", os.path.join(GOLD, "edge_r1"), out2])      # default: the reference's silence, exit 0
+    assert "Corrupt record" not in log
+    same_tree(out1, out2)
+
+
 @needs_ref
 def test_two_ranks_same_deal_as_reference(main_bin, edge_tree, tmp_path):
     """`mpirun -n 2` analogue: rank r takes sorted files r, r+2, ... and writes compressed_<r>.zwz (compression.cpp:31-41,157)."""
