@@ -74,8 +74,63 @@ static void decompress(const std::string &source_path, const std::string &output
     }
 }
 
+namespace {
+
+const char *kReadyMarker = "/.zwz_record_ready";
+
+// rank 0 only (main.cpp:104-129): the source must exist; the output directory is created when missing
+bool prepare_paths(const std::string &source_path, const std::string &output_path) {
+    namespace fs = std::filesystem;
+    std::error_code ec;
+    if (!fs::exists(source_path, ec)) {
+        std::cerr << "Source path does not exist.\n";
+        return false;
+    }
+    if (!fs::exists(output_path, ec)) {
+        if (mkdir(output_path.c_str(), 0777) == -1) {
+            perror("Failed to create output directory");
+            return false;
+        }
+        return true;
+    }
+    if (!fs::is_directory(output_path, ec)) {
+        std::cerr << "Output path is not a directory.\n";
+        return false;
+    }
+    return true;
+}
+
+// ZWZ_GPUS=N without an external launcher: ranks 1..N-1 are forked here, one process per GPU, before this process has
+// made any CUDA call. Returns the children (empty in a child).
+std::vector<pid_t> fork_ranks(int n) {
+    RunConfig &cfg = config();
+    std::vector<pid_t> kids;
+    cfg.world_size = n;
+    for (int r = 1; r < n; ++r) {
+        pid_t pid = fork();
+        if (pid == 0) {
+            cfg.world_rank = r;
+            const int ndev = visible_gpu_count();
+            cfg.device = ndev > 0 ? r % ndev : 0;
+            return {};
+        }
+        kids.push_back(pid);
+    }
+    return kids;
+}
+
+void print_summary(const std::string &operation, double seconds) { // main.cpp:148-156
+    std::cout << "========================================\n"
+              << "Operation: " << operation << '\n'
+              << "Processor Count: " << config().world_size << '\n'
+              << "Time Taken: " << seconds << " seconds\n"
+              << "========================================\n";
+}
+
+} // namespace
+
 int main(int argc, char *argv[]) {
-    double start_time = now_s();
+    const double start_time = now_s();
     config_from_env();
     RunConfig &cfg = config();
     timing_mark("configured");
@@ -84,52 +139,26 @@ int main(int argc, char *argv[]) {
         std::cerr << "Usage: " << argv[0] << " <compress/decompress> <source directory path> <output directory path>\n";
         return 1;
     }
-    std::string operation = argv[1], source_path = argv[2], output_path = argv[3];
+    const std::string operation = argv[1];
+    std::string source_path = argv[2], output_path = argv[3];
     remove_trailing_slash(source_path);
     remove_trailing_slash(output_path);
     std::cout << "source_path: " << source_path << '\n';
     std::cout << "output_path: " << output_path << '\n';
 
-    // self-launch: ZWZ_GPUS=N without an external launcher => fork ranks 1..N-1 (one process per GPU)
-    std::vector<pid_t> kids;
+    const bool compressing = operation == "compress";
+    if (cfg.world_rank == 0) {
+        if (!prepare_paths(source_path, output_path)) return 1;
+        if (compressing) std::remove((output_path + kReadyMarker).c_str());
+    }
     const char *g = std::getenv("ZWZ_GPUS");
-    int self_gpus = (g && cfg.world_size == 1) ? std::atoi(g) : 0;
-
-    if (cfg.world_rank == 0) { // main.cpp:104-129
-        struct stat path_stat {};
-        if (stat(source_path.c_str(), &path_stat) != 0) {
-            std::cerr << "Source path does not exist.\n";
-            return 1;
-        }
-        if (stat(output_path.c_str(), &path_stat) != 0) {
-            if (mkdir(output_path.c_str(), 0777) == -1) {
-                perror("Failed to create output directory");
-                return 1;
-            }
-        } else if (!S_ISDIR(path_stat.st_mode)) {
-            std::cerr << "Output path is not a directory.\n";
-            return 1;
-        }
-        if (operation == "compress") std::remove((output_path + "/.zwz_record_ready").c_str());
-    }
-    if (self_gpus > 1 && operation == "compress") {
-        cfg.world_size = self_gpus;
-        for (int r = 1; r < self_gpus; ++r) {
-            pid_t pid = fork(); // before any CUDA call in this process
-            if (pid == 0) {
-                cfg.world_rank = r;
-                int ndev = visible_gpu_count();
-                cfg.device = ndev > 0 ? r % ndev : 0;
-                kids.clear();
-                break;
-            }
-            kids.push_back(pid);
-        }
-    }
+    const int self_gpus = (g && cfg.world_size == 1) ? std::atoi(g) : 0;
+    std::vector<pid_t> kids;
+    if (self_gpus > 1 && compressing) kids = fork_ranks(self_gpus);
 
     int rc = 0;
     try {
-        if (operation == "compress") {
+        if (compressing) {
             compress(source_path, output_path);
         } else if (operation == "decompress") {
             decompress(source_path, output_path);
@@ -146,20 +175,15 @@ int main(int argc, char *argv[]) {
         std::cerr << "ZWZ_STRICT: " << stats().bad_records << " record(s) did not decode cleanly" << std::endl;
         rc = 4;
     }
-    if (self_gpus > 1 && cfg.world_rank != 0) _exit(rc);
+    if (self_gpus > 1 && compressing && cfg.world_rank != 0) _exit(rc); // a forked rank: no summary, no waiting
     for (pid_t k : kids) {
         int st = 0;
         waitpid(k, &st, 0);
-        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = rc ? rc : 3;
+        if ((!WIFEXITED(st) || WEXITSTATUS(st) != 0) && rc == 0) rc = 3;
     }
     if (cfg.world_rank == 0) {
-        if (operation == "compress") std::remove((output_path + "/.zwz_record_ready").c_str());
-        double total_time = now_s() - start_time;
-        std::cout << "========================================\n"
-                  << "Operation: " << operation << '\n'
-                  << "Processor Count: " << cfg.world_size << '\n'
-                  << "Time Taken: " << total_time << " seconds\n"
-                  << "========================================\n";
+        if (compressing) std::remove((output_path + kReadyMarker).c_str());
+        print_summary(operation, now_s() - start_time);
     }
     return rc;
 }

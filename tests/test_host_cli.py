@@ -139,6 +139,26 @@ def test_we_decompress_golden_archives(main_bin, name, tmp_path):
     assert log.count("MD5 mismatch for file") == man[name]["verdicts"]["mismatch"]
 
 
+@needs_ref
+def test_self_launch_one_process_per_gpu(main_bin, edge_tree, tmp_path):
+    """`ZWZ_GPUS=2 main compress` forks rank 1 itself (no MPI launcher): two archives with the reference's deal, and the
+    reference reads them back to the source tree."""
+    src, specs = edge_tree
+    arch, out = str(tmp_path / "arch"), str(tmp_path / "out")
+    log = run([main_bin, "compress", src, arch], {"ZWZ_GPUS": "2"})
+    assert sorted(f for f in os.listdir(arch) if f.endswith(".zwz")) == ["compressed_0.zwz", "compressed_1.zwz"]
+    assert "Processor Count: 2" in log and not os.path.exists(os.path.join(arch, ".zwz_record_ready"))
+    order = sorted(specs, key=lambda s: -s.size)
+    for r in (0, 1):
+        paths = []
+        for rec in zwz_format.parse(open(os.path.join(arch, f"compressed_{r}.zwz"), "rb").read()):
+            if rec.path not in paths:
+                paths.append(rec.path)
+        assert sorted(paths) == sorted(s.relpath for s in order[r::2])
+    run([MAIN_REF, "decompress", arch, out])
+    same_tree(src, out)
+
+
 def test_strict_mode_names_the_records_zlib_would_have_rejected(main_bin, tmp_path):
     """ZWZ_STRICT=1: the reference ignores zlib's return codes (decompression.cpp:31); with the flag
     every record that does not reach a clean end of stream is named and the exit code is 4. Same bytes are written either way.
