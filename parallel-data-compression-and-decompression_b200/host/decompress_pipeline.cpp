@@ -26,6 +26,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <unordered_map>
 #include <sstream>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -74,9 +75,13 @@ struct Group {
 
 // decompression.cpp:65-92
 void parse_archive(const Span &a, std::vector<FileState> &files) {
-    std::map<std::string, size_t> index;
-    std::map<std::string, int> expected;                 // the reference's expected_sequence_id, simulated
-    std::map<std::string, std::vector<int>> pending;     // seqs sitting in the heap
+    struct Heap {                 // the reference's per-path reader state, simulated to know which verdicts it would print
+        int expected = 0;         // expected_sequence_id
+        std::vector<int> pending; // sequence ids sitting in its min-heap
+    };
+    std::unordered_map<std::string, size_t> index;
+    std::vector<Heap> heaps;
+    size_t cur = (size_t) -1; // records of one path are consecutive in every archive a writer produces: skip the lookup then
     size_t o = 0;
     const size_t n = a.size();
     while (o + 4 <= n) {
@@ -85,7 +90,7 @@ void parse_archive(const Span &a, std::vector<FileState> &files) {
         if (o + 8 > n) break;
         std::memcpy(&path_length, a.data() + o + 4, 4);
         if (path_length < 0 || o + 8 + (size_t) path_length + 5 > n) break;
-        std::string relpath((const char *) a.data() + o + 8, (size_t) path_length);
+        const char *path_bytes = (const char *) a.data() + o + 8;
         int sequence_id;
         std::memcpy(&sequence_id, a.data() + o + 8 + path_length, 4);
         bool is_last = a[o + 12 + path_length] != 0;
@@ -93,54 +98,56 @@ void parse_archive(const Span &a, std::vector<FileState> &files) {
         size_t p0 = o + 13 + (size_t) path_length;
         if (payload < 0 || p0 + (size_t) payload > n) break;
         o = p0 + (size_t) payload;
-        std::string md5;
+        const char *md5_bytes = nullptr;
+        size_t md5_len = 0;
         if (is_last) {
-            if (o + MD5_DATA_SIZE > n) {
-                md5.assign((const char *) a.data() + o, n - o);
-                o = n;
-            } else {
-                md5.assign((const char *) a.data() + o, MD5_DATA_SIZE);
-                o += MD5_DATA_SIZE;
+            md5_bytes = (const char *) a.data() + o;
+            md5_len = o + MD5_DATA_SIZE > n ? n - o : MD5_DATA_SIZE;
+            o += md5_len;
+        }
+        if (cur == (size_t) -1 || files[cur].relpath.size() != (size_t) path_length ||
+            std::memcmp(files[cur].relpath.data(), path_bytes, (size_t) path_length) != 0) {
+            std::string relpath(path_bytes, (size_t) path_length);
+            auto it = index.find(relpath);
+            if (it == index.end()) {
+                it = index.emplace(relpath, files.size()).first;
+                files.emplace_back();
+                files.back().relpath = std::move(relpath);
+                heaps.emplace_back();
             }
+            cur = it->second;
         }
-        auto it = index.find(relpath);
-        if (it == index.end()) {
-            it = index.emplace(relpath, files.size()).first;
-            files.emplace_back();
-            files.back().relpath = relpath;
-            expected[relpath] = 0;
-        }
-        FileState &fsx = files[it->second];
+        FileState &fsx = files[cur];
         fsx.recs.push_back({(uint64_t) p0, (uint32_t) payload, sequence_id, is_last});
-        if (is_last) fsx.stored_md5 = md5;
-        // simulate the heap to know whether the reference would print a verdict for this file
-        int &exp = expected[relpath];
-        auto &pend = pending[relpath];
-        if (exp == sequence_id) {
-            ++exp;
+        if (is_last) fsx.stored_md5.assign(md5_bytes, md5_len);
+        Heap &h = heaps[cur];
+        if (h.expected == sequence_id) {
+            ++h.expected;
             for (;;) {
-                auto m = std::min_element(pend.begin(), pend.end());
-                if (m == pend.end() || *m != exp) break;
-                pend.erase(m);
-                ++exp;
+                auto m = std::min_element(h.pending.begin(), h.pending.end());
+                if (m == h.pending.end() || *m != h.expected) break;
+                h.pending.erase(m);
+                ++h.expected;
             }
-            if (is_last && exp == sequence_id + 1 && pend.empty()) fsx.verdict_in_order = true;
+            if (is_last && h.expected == sequence_id + 1 && h.pending.empty()) fsx.verdict_in_order = true;
         } else {
-            pend.push_back(sequence_id);
+            h.pending.push_back(sequence_id);
         }
     }
+    // the records a file receives: sequence ids 0, 1, 2, ... up to the first missing one, first occurrence of each id
     for (auto &f : files) {
-        int want = 0;
-        for (;;) {
-            const Rec *hit = nullptr;
-            for (const auto &r : f.recs)
-                if (r.seq == want) {
-                    hit = &r;
-                    break;
-                }
-            if (!hit) break;
-            f.ordered.push_back(*hit);
-            ++want;
+        bool in_order = true;
+        for (size_t i = 0; i < f.recs.size() && in_order; ++i) in_order = f.recs[i].seq == (int) i;
+        if (in_order) { // what every writer produces; also keeps a 262 149-record file linear
+            f.ordered = f.recs;
+        } else {
+            std::unordered_map<int, size_t> first;
+            for (size_t i = 0; i < f.recs.size(); ++i) first.emplace(f.recs[i].seq, i);
+            for (int want = 0;; ++want) {
+                auto it = first.find(want);
+                if (it == first.end()) break;
+                f.ordered.push_back(f.recs[it->second]);
+            }
         }
         f.complete = !f.ordered.empty() && f.ordered.back().last;
     }
