@@ -154,12 +154,15 @@ void parse_archive(const Span &a, std::vector<FileState> &files) {
 }
 
 
-void ensure_parent(const std::string &file_path) {
-    fs::path dir = fs::path(file_path).parent_path();
-    if (!dir.empty() && !fs::exists(dir)) {
-        std::error_code ec;
-        fs::create_directories(dir, ec);
-    }
+// `last_dir` remembers the directory of the previous call (files of one directory are consecutive in an archive): one
+// existence check per directory instead of one per file
+void ensure_parent(const std::string &file_path, std::string &last_dir) {
+    const size_t slash = file_path.find_last_of('/');
+    if (slash == std::string::npos || slash == 0) return;
+    if (last_dir.size() == slash && file_path.compare(0, slash, last_dir) == 0) return;
+    last_dir.assign(file_path, 0, slash);
+    std::error_code ec;
+    if (!fs::exists(last_dir, ec)) fs::create_directories(last_dir, ec);
 }
 
 // console text of one group, released in group order
@@ -338,7 +341,7 @@ class Worker {
         for (size_t f = grp.first; f < grp.first + grp.count; ++f) {
             FileState &fsx = a.files[f];
             std::string file_path = job_.output_dir + "/" + fsx.relpath;
-            ensure_parent(file_path);
+            ensure_parent(file_path, last_dir_);
             std::FILE *o = std::fopen(file_path.c_str(), "wb");
             if (!o) {
                 con.err << "Error creating output file: " << file_path << "\n";
@@ -366,7 +369,7 @@ class Worker {
     void big_file(Archive &a, FileState &fsx, Console &con, RunStats &st) {
         const RunConfig &cfg = config();
         std::string file_path = job_.output_dir + "/" + fsx.relpath;
-        ensure_parent(file_path);
+        ensure_parent(file_path, last_dir_);
         std::FILE *o = std::fopen(file_path.c_str(), "wb");
         if (!o) {
             con.err << "Error creating output file: " << file_path << "\n";
@@ -405,6 +408,7 @@ class Worker {
     Job &job_;
     zwz_ctx *ctx_;
     PinnedBuf in_, out_;
+    std::string last_dir_;
 };
 
 bool map_archive(Archive &a) {
