@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py — the hot path of BASELINE.json on synthetic corpora of the named shapes.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--files F]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c5] [--files F]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...        # the reference's CPU path (zlib L6 / zlib inflate / OpenSSL MD5) on host cores
+  python bench.py --impl reference ...        # the UNMODIFIED reference binary (zlib L6 / zlib inflate / OpenSSL MD5) on host cores
 
 A "step" is one pass of the hot path over the rank's shard of the workload:
   compress side   deflate of every 65 535-byte chunk (compression.cpp:119-134) + MD5 of every source file (:95-103)
   decompress side inflate of every record (decompression.cpp:11-37) + MD5 of every output file (:136)
-`value` is uncompressed bytes of the whole job / device time of that step with the inputs already resident in HBM
-(CUDA events on the launching stream, max over ranks); `e2e` is the same step from PINNED HOST buffers through the same
-C ABI with the H2D/D2H copies inside the timed region. Default workload = BASELINE.json configs[1] (C2: 370 000 image-like
-files, ~2.5 GB, every file one sub-65 535-byte chunk). Multi-GPU: the reference's policy — sort by size descending, rank r
-takes sorted files r, r+N, ... (file_sort.cpp:30-31, compression.cpp:31-41); no data-path collective, one NCCL
-all-gather of per-rank counters; per-rank work is fixed as N grows => "scaling": "weak".
+`value`  = uncompressed bytes of the whole job / device time of that step with the inputs already resident in HBM (CUDA
+           events on the launching stream, max over ranks).
+`e2e`    = the same step through the HOST-BUFFER plugin calls the C++ host (`main`) makes — zwz_compress_files +
+           zwz_decompress_records (zwz_deflate_batch + zwz_inflate_batch for the single-file shape) — from page-locked host
+           buffers back into page-locked host buffers: every H2D/D2H copy, arena and descriptor handling of the library is
+           inside the timed region; W worker contexts per rank, like `main` (host/pipeline.hpp).
+Workloads (BASELINE.json `configs`): c2 (default; configs[1]: 370 000 image-like files, ~2.5 GB), c1 (configs[0] shape),
+c3 (configs[2]: one log/text file, `--files` bytes, 16 GiB = 17179869184), c5 (configs[4]: 64 GB mixed corpus cut over the
+N GPUs: strong scaling). The default c2 line also carries short device-timed C1- and C3-shaped passes (`extra_workloads`).
+Multi-GPU: the reference's policy — sort by size descending, rank r takes sorted files r, r+N, ... (file_sort.cpp:30-31,
+compression.cpp:31-41); no data-path collective, one NCCL all-gather of per-rank counters.
 """
 import argparse
 import json
@@ -34,38 +39,55 @@ from tools import corpus  # noqa: E402
 CHUNK = 65535
 METRIC = "deflate/inflate GB/s (uncompressed)"
 UNIT = "GB/s"
+C3_PERIOD = 32 << 20
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# workload: every rank builds ITS shard only. File sizes come from the global list (N x the single-GPU corpus) sorted by
-# size descending and dealt round-robin, exactly the reference's distribution rule; contents are generated per rank.
+# workload: every rank builds ITS shard only. A shard is `period` bytes of generated content (`unit`) repeated up to `U`
+# bytes (period == U for the shapes that are generated in full); `foffs` are the file boundaries inside the U bytes.
 # ---------------------------------------------------------------------------------------------------------------------
-def build_shard(workload: str, files: int, rank: int, world: int):
+class Shard:
+    def __init__(self, unit, U, foffs, desc, scaling="weak"):
+        self.unit = unit            # np.uint8[period]
+        self.period = len(unit)
+        self.U = int(U)
+        self.foffs = np.asarray(foffs, dtype=np.int64)
+        self.desc = desc
+        self.scaling = scaling
+        self.periodic = self.period < self.U
+
+    def host_bytes(self, lo, hi):
+        """bytes [lo, hi) of the shard as a numpy array (copies when the range wraps the period)"""
+        if not self.periodic:
+            return self.unit[lo:hi]
+        idx0 = lo % self.period
+        if idx0 + (hi - lo) <= self.period:
+            return self.unit[idx0:idx0 + hi - lo]
+        reps = (idx0 + hi - lo + self.period - 1) // self.period
+        return np.tile(self.unit, reps)[idx0:idx0 + hi - lo]
+
+
+def build_shard(workload: str, files: int, rank: int, world: int) -> Shard:
     seed = corpus.BASE_SEED
     if workload == "c2":
-        # content keyed by (seed, rank, directory); sizes from the global size-sorted deal
+        # sizes from the global size-sorted deal; content keyed by (seed, rank, directory)
         all_sizes = corpus.c2_sizes(files * world, seed)
         order = np.argsort(-all_sizes, kind="stable")
         mine = order[rank::world]
         buf, offs, sizes = corpus.c2_buffer(len(mine), seed + 7919 * rank)
-        # c2_buffer draws its own sizes; re-cut the buffer to the dealt sizes (same generator, same class mix): regenerate
-        # with the dealt sizes so the shard is size-descending like the reference's record file
         want = all_sizes[mine]
         tot = int(want.sum())
         if tot > len(buf):
             extra, _, _ = corpus.c2_buffer(int((tot - len(buf)) // 6000 + 1000), seed + 7919 * rank + 1)
             buf = np.concatenate([buf, extra])
-        buf = buf[:tot]
+        buf = np.ascontiguousarray(buf[:tot])
         foffs = np.zeros(len(want) + 1, dtype=np.int64)
         np.cumsum(want, out=foffs[1:])
-        desc = f"C2: {files} image-like files/GPU (70% JPEG-like, 30% bitmap-like), one chunk each"
-        return buf, foffs, desc
+        return Shard(buf, tot, foffs, f"C2: {files} image-like files/GPU (70% JPEG-like, 30% bitmap-like), one chunk each")
     if workload == "c3":
         size = files  # bytes
-        unit = corpus.gen_text(min(size, 32 << 20), seed, 0x100000 + rank)
-        reps = (size + len(unit) - 1) // len(unit)
-        buf = np.tile(unit, reps)[:size]
-        return buf, np.array([0, size], dtype=np.int64), f"C3: one {size}-byte log/text file per GPU, 65 535-byte chunks (32 MiB period)"
+        unit = corpus.gen_text(min(size, C3_PERIOD), seed, 0x100000 + rank)
+        return Shard(unit, size, [0, size], f"C3: one {size}-byte log/text file per GPU, 65 535-byte chunks ({len(unit) >> 20} MiB period)")
     if workload == "c1":
         buf, offs, specs = corpus.mixed_buffer(files, seed + 1 + rank, 4096, 16 << 20)
         sizes = np.diff(offs)
@@ -73,7 +95,27 @@ def build_shard(workload: str, files: int, rank: int, world: int):
         parts = [buf[offs[i]:offs[i + 1]] for i in order]
         foffs = np.zeros(len(order) + 1, dtype=np.int64)
         np.cumsum(sizes[order], out=foffs[1:])
-        return np.concatenate(parts), foffs, f"C1-shaped: {files} bytes of mixed T/S/I/R files per GPU, size-descending"
+        return Shard(np.concatenate(parts), int(foffs[-1]), foffs, f"C1-shaped: {files} bytes of mixed T/S/I/R files per GPU, size-descending")
+    if workload == "c5":
+        # BASELINE configs[4]: 64 GB of C1-generator files (seed 597) cut over the N GPUs. Generating 64 GB takes half an hour
+        # of host time, so each rank generates a POOL of such files (seed 597 + rank, size-descending) and its shard is that
+        # pool's file list repeated until the rank's share (total / N) is reached. Chunks are independent streams, so the
+        # repetition changes nothing for the kernels.
+        total = files
+        share = total // world
+        pool_bytes = min(share, 768 << 20)
+        buf, offs, specs = corpus.mixed_buffer(pool_bytes, seed + 1 + rank, 4096, 16 << 20)
+        sizes = np.diff(offs)
+        order = np.argsort(-sizes, kind="stable")
+        unit = np.concatenate([buf[offs[i]:offs[i + 1]] for i in order])
+        psz = sizes[order]
+        reps = max(1, int(round(share / len(unit))))
+        fsz = np.tile(psz, reps)
+        foffs = np.zeros(len(fsz) + 1, dtype=np.int64)
+        np.cumsum(fsz, out=foffs[1:])
+        return Shard(unit, int(foffs[-1]), foffs,
+                     f"C5: {total} bytes of mixed T/S/I/R files (C1 generator, seed 597) cut over {world} GPU(s); per-GPU pool of {len(unit)} bytes x {reps}",
+                     scaling="strong")
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -133,8 +175,7 @@ class ClockSampler:
 # OpenSSL MD5 in 1024-byte updates), fanned out over host threads (ctypes releases the GIL).
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_step(buf, foffs, coff, clen, threads, do_md5=True):
-    """One full step (compress side + decompress side) on the CPU. Returns (seconds, compressed_bytes)."""
-    import ctypes as C
+    """One full step (compress side + decompress side) on the CPU. Returns (seconds, compressed_bytes, ok)."""
     from concurrent.futures import ThreadPoolExecutor
 
     import oracle_lib as O
@@ -186,14 +227,14 @@ def cpu_step(buf, foffs, coff, clen, threads, do_md5=True):
     return dt, int(out_len.sum()), ok
 
 
-def reference_binary_step(main_ref, sb, so, cores, workload):
+def reference_binary_step(main_ref, sb, so, cores):
     """Materialise the sample as a directory tree in RAM and return (step(), P): step() runs `main_ref compress` with P
     concurrently running emulated ranks (the MPI stub reads ZWZ_STUB_RANK/SIZE) and then `main_ref decompress`, and returns
     (seconds, archive bytes). The reference's per-file stdout goes to /dev/null."""
+    import atexit
     import shutil
     import tempfile
     root = tempfile.mkdtemp(prefix="zwz_ref_", dir="/dev/shm")
-    import atexit
     atexit.register(lambda: shutil.rmtree(root, ignore_errors=True))
     src = os.path.join(root, "w", "src")
     nf = len(so) - 1
@@ -232,24 +273,186 @@ def reference_binary_step(main_ref, sb, so, cores, workload):
     return step, P
 
 
-def sample_of(buf, foffs, target_bytes):
+def sample_of(sh: Shard, target_bytes):
     """Bounded sample of the same workload: whole files taken evenly across the size-sorted shard."""
+    foffs = sh.foffs
     nf = len(foffs) - 1
-    tot = int(foffs[-1])
+    tot = sh.U
     if tot <= target_bytes:
-        return buf, foffs, "whole shard"
+        return np.ascontiguousarray(sh.host_bytes(0, tot)), foffs.copy(), "whole shard"
     if nf == 1:
-        n = (target_bytes // CHUNK) * CHUNK
-        return buf[:n], np.array([0, n], dtype=np.int64), f"first {n} bytes of the file"
-    stride = max(1, int(tot // target_bytes))
+        n = max(1, int(target_bytes // CHUNK)) * CHUNK
+        return np.ascontiguousarray(sh.host_bytes(0, n)), np.array([0, n], dtype=np.int64), f"first {n} bytes of the file"
+    stride = max(1, int(round(tot / target_bytes)))
     idx = np.arange(0, nf, stride)
     sizes = np.diff(foffs)[idx]
     so = np.zeros(len(idx) + 1, dtype=np.int64)
     np.cumsum(sizes, out=so[1:])
     sb = np.empty(int(so[-1]), dtype=np.uint8)
     for k, i in enumerate(idx):
-        sb[so[k]:so[k + 1]] = buf[foffs[i]:foffs[i + 1]]
+        sb[so[k]:so[k + 1]] = sh.host_bytes(int(foffs[i]), int(foffs[i + 1]))
     return sb, so, f"every {stride}-th file of the size-sorted shard ({len(idx)} files, {int(so[-1])} bytes)"
+
+
+def global_totals(workload: str, files: int, world: int):
+    """(chunks, files, bytes) of the WHOLE job over `world` GPUs, from sizes alone (no contents generated): both arms put the
+    same numbers into `config`."""
+    seed = corpus.BASE_SEED
+
+    def chunks_of(sizes):
+        return int((np.asarray(sizes, dtype=np.int64) // CHUNK + 1).sum())
+    if workload == "c2":
+        sz = corpus.c2_sizes(files * world, seed)
+        return chunks_of(sz), len(sz), int(sz.sum())
+    if workload == "c3":
+        return world * (files // CHUNK + 1), world, world * files
+    if workload == "c1":
+        sz = [s.size for r in range(world) for s in corpus.mixed_specs(files, seed + 1 + r, 4096, 16 << 20)]
+        return chunks_of(sz), len(sz), int(sum(sz))
+    if workload == "c5":
+        share = files // world
+        pool_bytes = min(share, 768 << 20)
+        nch = nfi = tot = 0
+        for r in range(world):
+            psz = np.array([s.size for s in corpus.mixed_specs(pool_bytes, seed + 1 + r, 4096, 16 << 20)], dtype=np.int64)
+            reps = max(1, int(round(share / int(psz.sum()))))
+            nch += reps * chunks_of(psz)
+            nfi += reps * len(psz)
+            tot += reps * int(psz.sum())
+        return nch, nfi, tot
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def config_of(args, sh: Shard, world):
+    """Workload description shared VERBATIM by both arms (`--impl ours` and `--impl reference`)."""
+    n_chunks_all, nf_all, U_all = global_totals(args.workload, args.files, world)
+    return {"workload": sh.desc, "chunks": int(n_chunks_all), "files": int(nf_all), "uncompressed_bytes": int(U_all),
+            "l2": "inputs (>= 2 GB/GPU) exceed the 126 MB L2", "level": args.level,
+            "md5": bool(args.do_md5),
+            "parallelism": f"files dealt size-descending round-robin over {world} GPU(s)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def records_of(res, poff, raw_off):
+    """record table (one per stream; chunks cut by the split rule give two) from the deflate results"""
+    split = res["len1"] > 0
+    if not split.any():
+        return poff[:-1], res["len0"], raw_off, None
+    k = np.nonzero(split)[0]
+    r_off = np.insert(poff[:-1], k + 1, poff[:-1][k] + res["len0"][k].astype(np.uint64))
+    r_len = np.insert(res["len0"], k + 1, res["len1"][k])
+    r_raw = np.insert(raw_off[:-1], k + 1, raw_off[:-1][k] + res["raw0"][k].astype(np.uint64))
+    return r_off, r_len, np.concatenate([r_raw, raw_off[-1:]]), k
+
+
+def host_roundtrip(w, d, clen, raw_ptr, comp_ptr, comp_cap, back_ptr, level, do_md5):
+    """One part of the shard through the host-buffer plugin calls (what `main` does per batch): compress side into the
+    buffer at comp_ptr, then the decompress side from that buffer into back_ptr. Returns the compressed bytes."""
+    c0, c1, b0, b1 = d["c0"], d["c1"], d["b0"], d["b1"]
+    if "foff" in d:
+        nfp = d["f1"] - d["f0"]
+        # compress side: compression.cpp:106-148 for the files of this part (chunking, deflate, MD5 of every file)
+        poff, res, dg1 = w.compress_files_into(raw_ptr, d["foff"], level, comp_ptr, comp_cap, want_md5=do_md5)
+        # decompress side: decompression.cpp:100-151 for the records just made
+        r_off, r_len, _, k = records_of(res, poff, np.zeros(c1 - c0 + 1, dtype=np.uint64))
+        rfile = d["rfile"] if k is None else np.insert(d["rfile"], k + 1, d["rfile"][k])
+        rcap = np.full(len(r_off), CHUNK, dtype=np.uint32)
+        foff2, rl, st, dg2 = w.decompress_records_into(comp_ptr, r_off, r_len, rcap, rfile, nfp, back_ptr, b1 - b0, want_md5=do_md5)
+        assert np.array_equal(foff2, d["foff"]), "file layout after decompress"
+        if do_md5:
+            assert np.array_equal(dg1, dg2), "MD5 verify failed"
+    else:
+        poff, res = w.deflate_batch_into(raw_ptr, d["coff"], clen[c0:c1], comp_ptr, comp_cap, level)
+        r_off, r_len, r_raw_off, _ = records_of(res, poff, d["roff"])
+        rl, st = w.inflate_batch_into(comp_ptr, r_off, r_len, back_ptr, r_raw_off, 0)
+    assert (st == 0).all()
+    return int(poff[-1])
+
+
+def part_descriptors(sh, coff, clen, cfile, raw_off, slot_off, part_chunk, part_file, wrap):
+    """Per-part descriptors that do not depend on results (prepared once, outside the timed region: `main` plans its batches
+    up front the same way)."""
+    out = []
+    nparts = len(part_chunk) - 1
+    for i in range(nparts):
+        c0, c1 = int(part_chunk[i]), int(part_chunk[i + 1])
+        b0, b1 = int(raw_off[c0]), int(raw_off[c1])
+        d = {"c0": c0, "c1": c1, "b0": b0, "b1": b1, "y0": (b0 % wrap) if sh.periodic else b0, "hc": int(slot_off[c0])}
+        if part_file is not None:
+            f0, f1 = int(part_file[i]), int(part_file[i + 1])
+            d.update(f0=f0, f1=f1, foff=(sh.foffs[f0:f1 + 1] - b0).astype(np.uint64), rfile=(cfile[c0:c1] - f0).astype(np.uint32))
+        else:
+            d.update(coff=(coff[c0:c1] - np.uint64(b0)).astype(np.uint64), roff=(raw_off[c0:c1 + 1] - np.uint64(b0)).astype(np.uint64))
+        out.append(d)
+    return out
+
+
+def device_pass(torch, zwz_b200, ctx, stream, sh: Shard, level, do_md5, steps, warmup):
+    """Short device-timed pass over a small shard (for the `extra_workloads` keys): returns a dict of rates."""
+    U = sh.U
+    coff, clen, cfile, cseq = zwz_b200.chunk_table(sh.foffs)
+    n = len(coff)
+    slot = zwz_b200.deflate_bound(clen)
+    slot_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(slot, out=slot_off[1:])
+    raw_off = np.concatenate([coff, [np.uint64(U)]]).astype(np.uint64)
+    f_off = sh.foffs[:-1].astype(np.uint64)
+    f_len = np.diff(sh.foffs).astype(np.uint64)
+    d_raw = torch.empty(U + 64, dtype=torch.uint8, device="cuda")
+    fill_device(torch, d_raw, sh)
+    d_slots = torch.empty(int(slot_off[-1]) + 64, dtype=torch.uint8, device="cuda")
+    d_packed = torch.empty(int(slot_off[-1]) + 64, dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(U + 64, dtype=torch.uint8, device="cuda")
+    st = {}
+
+    def step():
+        res = ctx.deflate_batch_device(d_raw.data_ptr(), coff, clen, d_slots.data_ptr(), slot_off[:-1], level, stream)
+        if do_md5:
+            st["dg1"] = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream)
+        poff = ctx.pack_streams_device(d_slots.data_ptr(), slot_off[:-1], res, d_packed.data_ptr(), stream)
+        r_off, r_len, r_raw_off, _ = records_of(res, poff, raw_off)
+        rl, s = ctx.inflate_batch_device(d_packed.data_ptr(), r_off, r_len, d_back.data_ptr(), r_raw_off, 0, stream)
+        if do_md5:
+            st["dg2"] = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream)
+        st.update(res=res, s=s)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    assert (st["s"] == 0).all() and torch.equal(d_back[:U], d_raw[:U])
+    ctx.profile_enable(True)
+    ctx.profile_read(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    prof = ctx.profile_read(True)
+    ctx.profile_enable(False)
+    C = int(st["res"]["len0"].sum() + st["res"]["len1"].sum())
+    k = {name: v[0] / steps for name, v in prof.items()}
+    out = {"workload": sh.desc, "uncompressed_bytes": U, "chunks": n, "files": len(f_off), "steps": steps, "value": U / (ms * 1e-3) / 1e9, "ms_per_step": ms,
+           "ratio": U / max(C, 1), "deflate_gbs": U / ((k["lz_match"] + k["deflate_encode"]) * 1e-3) / 1e9,
+           "inflate_gbs": U / (k["inflate"] * 1e-3) / 1e9, "kernel_ms_per_step": k, "md5": bool(do_md5)}
+    del d_raw, d_slots, d_packed, d_back
+    torch.cuda.empty_cache()
+    return out
+
+
+def fill_device(torch, d_raw, sh: Shard):
+    """shard bytes -> device tensor (tiled on the device when the shard is periodic)"""
+    U = sh.U
+    if not sh.periodic:
+        d_raw[:U].copy_(torch.from_numpy(sh.unit), non_blocking=False)
+        return
+    d_unit = torch.from_numpy(sh.unit).cuda()
+    P = sh.period
+    for o in range(0, U, P):
+        k = min(P, U - o)
+        d_raw[o:o + k].copy_(d_unit[:k])
+    del d_unit
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -259,23 +462,25 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c1"])
-    ap.add_argument("--files", type=int, default=0, help="c2: files per GPU (default 370000); c3/c1: bytes per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c1", "c5"])
+    ap.add_argument("--files", type=int, default=0, help="c2: files per GPU (default 370000); c3/c1: bytes per GPU; c5: total bytes (default 64e9)")
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
+    ap.add_argument("--ref-sample-mb", type=float, default=0.0, help="--impl reference: sample size (default: 1 GB at 25 steps, scaled so the run ends in minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C1/C3-shaped device passes of the default c2 line")
     ap.add_argument("--e2e-workers", type=int, default=0, help="end-to-end leg: worker contexts (stream + buffers each) per rank; 0 = min(6, host cores / ranks), at least 2")
     ap.add_argument("--e2e-parts", type=int, default=32, help="end-to-end leg: parts the shard is cut into")
     ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
-                    help="auto: on for c2/c1 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
-                         "the MD5 of ONE file is a single serial chain, one lane, ~0.1 GB/s)")
+                    help="auto: on for c2/c1/c5 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
+                         "the MD5 of ONE file is a single serial chain, one lane, ~0.13 GB/s)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
     if args.files == 0:
-        args.files = {"c2": 370_000, "c3": 2 << 30, "c1": 2 << 30}[args.workload]
+        args.files = {"c2": 370_000, "c3": 2 << 30, "c1": 2 << 30, "c5": 64_000_000_000}[args.workload]
 
-    do_md5 = args.md5 == "on" or (args.md5 == "auto" and args.workload != "c3")
+    args.do_md5 = do_md5 = args.md5 == "on" or (args.md5 == "auto" and args.workload != "c3")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -285,14 +490,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        buf, foffs, desc = build_shard(args.workload, args.files, 0, 1)
-        target = int(args.cpu_sample_mb * 1e6) if args.cpu_sample_mb else int(min(8e6 * cores, 400e6))
-        sb, so, what = sample_of(buf, foffs, target)
+        # same workload object as rank 0 of our arm builds (world = --gpus, so that config matches ours at every N)
+        sh = build_shard(args.workload, args.files, 0, max(1, args.gpus))
+        cfg = config_of(args, sh, max(1, args.gpus))
+        if args.ref_sample_mb:
+            target = int(args.ref_sample_mb * 1e6)
+        else:
+            # about 0.017 GB/s per core end to end (round 1: 0.266 GB/s on 16 cores); aim at <= ~150 s for all steps
+            target = int(min(sh.U, max(0.25e9, min(1.0e9, 150.0 * 0.017e9 * cores / (args.steps + args.warmup)))))
+        sb, so, what = sample_of(sh, target)
         main_ref = os.path.join(ROOT, "oracle", "_ref", "main_ref")
         if os.path.exists(main_ref) and os.path.isdir("/dev/shm"):
             kind = "reference"
             step = "UNMODIFIED reference binary (oracle/_ref/main_ref): compress with P emulated MPI ranks + decompress (1 process, OpenMP over archives) on a RAM-backed tree"
-            run_step, P = reference_binary_step(main_ref, sb, so, cores, args.workload)
+            run_step, P = reference_binary_step(main_ref, sb, so, cores)
             what += f"; written as files under /dev/shm; compress ranks = {P}"
         else:
             kind = "port"
@@ -308,8 +519,8 @@ def main():
         t = sum(times)
         val = len(sb) * len(times) / t / 1e9
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": {"workload": desc, "step": step},
+                "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": sh.scaling, "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": cfg, "pipeline": {"step": step},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": what,
                                  "ratio": len(sb) / max(comp, 1)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -330,8 +541,9 @@ def main():
     torch.cuda.set_stream(main_stream)       # everything below (events, copies, our kernels) is ordered on this stream
     stream = main_stream.cuda_stream
 
-    buf, foffs, desc = build_shard(args.workload, args.files, rank, world)
-    U = int(foffs[-1])
+    sh = build_shard(args.workload, args.files, rank, world)
+    U = sh.U
+    foffs = sh.foffs
     nf = len(foffs) - 1
     coff, clen, cfile, cseq = zwz_b200.chunk_table(foffs)
     n = len(coff)
@@ -342,16 +554,15 @@ def main():
     f_off = foffs[:-1].astype(np.uint64)
     f_len = np.diff(foffs).astype(np.uint64)
 
-    h_raw = torch.empty(U, dtype=torch.uint8, pin_memory=True)
-    h_raw.numpy()[:] = buf
-    h_back = torch.empty(U, dtype=torch.uint8, pin_memory=True)
-    h_comp = torch.empty(int(slot_off[-1]), dtype=torch.uint8, pin_memory=True)
     d_raw = torch.empty(U + 64, dtype=torch.uint8, device="cuda")
     d_slots = torch.empty(int(slot_off[-1]) + 64, dtype=torch.uint8, device="cuda")
-    d_packed = torch.empty(int(slot_off[-1]) + 64, dtype=torch.uint8, device="cuda")
     d_back = torch.empty(U + 64, dtype=torch.uint8, device="cuda")
-    d_raw[:U].copy_(h_raw, non_blocking=True)
+    fill_device(torch, d_raw, sh)
     torch.cuda.synchronize()
+    # the packed buffer is sized from a first deflate (a 16 GiB text file packs into ~6 GB; slot capacity would be 16 GiB more)
+    res0 = ctx.deflate_batch_device(d_raw.data_ptr(), coff, clen, d_slots.data_ptr(), slot_off[:-1], args.level, stream)
+    C0 = int(res0["len0"].sum() + res0["len1"].sum())
+    d_packed = torch.empty(C0 + 4096, dtype=torch.uint8, device="cuda")
 
     state = {}
 
@@ -360,89 +571,69 @@ def main():
         res = ctx.deflate_batch_device(d_raw.data_ptr(), coff, clen, d_slots.data_ptr(), slot_off[:-1], args.level, stream)
         dg1 = ctx.md5_batch_device(d_raw.data_ptr(), f_off, f_len, stream) if do_md5 else None
         poff = ctx.pack_streams_device(d_slots.data_ptr(), slot_off[:-1], res, d_packed.data_ptr(), stream)
-        # records: one per stream (split chunks give two)
-        r_off, r_len, r_raw_off = records_of(res, poff, raw_off)
+        r_off, r_len, r_raw_off, _ = records_of(res, poff, raw_off)   # records: one per stream (split chunks give two)
         rl, st = ctx.inflate_batch_device(d_packed.data_ptr(), r_off, r_len, d_back.data_ptr(), r_raw_off, 0, stream)
         dg2 = ctx.md5_batch_device(d_back.data_ptr(), f_off, f_len, stream) if do_md5 else None
         state.update(res=res, dg1=dg1, dg2=dg2, rl=rl, st=st, poff=poff, r_raw_off=r_raw_off)
 
-    def records_of(res, poff, raw_off):
-        split = res["len1"] > 0
-        if not split.any():
-            return poff[:-1], res["len0"], raw_off
-        k = np.nonzero(split)[0]
-        r_off = np.insert(poff[:-1], k + 1, poff[:-1][k] + res["len0"][k].astype(np.uint64))
-        r_len = np.insert(res["len0"], k + 1, res["len1"][k])
-        r_raw = np.insert(raw_off[:-1], k + 1, raw_off[:-1][k] + res["raw0"][k].astype(np.uint64))
-        return r_off, r_len, np.concatenate([r_raw, raw_off[-1:]])
-
-    # ---- end-to-end: W workers (own zwz ctx + CUDA stream + device buffers each) take parts of the shard in turn, so the
-    # H2D of one part, the kernels of another and the D2H of a third overlap (PCIe is full duplex). Every byte still starts in
-    # pinned host memory and ends in pinned host memory inside the timed region.
-    import threading
+    # ---- end-to-end through the host-buffer plugin calls: W workers (own zwz ctx = own stream + arenas, like `main`'s worker
+    # pool) take parts of the shard in turn, so the H2D of one part, the kernels of another and the D2H of a third overlap.
+    # Every byte starts in page-locked host memory and ends in page-locked host memory inside the timed region.
     from concurrent.futures import ThreadPoolExecutor
     W = args.e2e_workers if args.e2e_workers > 0 else max(2, min(6, (os.cpu_count() or 16) // max(world, 1)))
     first_chunk_of_file = np.concatenate([[0], np.cumsum(np.bincount(cfile, minlength=nf))]).astype(np.int64)
     if nf > 1:   # cut on file boundaries (MD5 needs whole files), parts of about equal bytes
-        want = min(args.e2e_parts, max(1, nf // 2000))
+        want = min(max(args.e2e_parts, int(U // (768 << 20))), max(1, nf // 8))
         part_file = np.unique(np.searchsorted(foffs, np.linspace(0, U, want + 1)))
         part_file[0], part_file[-1] = 0, nf
         part_file = np.unique(part_file)
         part_chunk = first_chunk_of_file[part_file]
-    elif do_md5:  # one file and its MD5 wanted: a single part (the digest is one serial chain anyway)
-        part_file = np.array([0, 1])
-        part_chunk = np.array([0, n], dtype=np.int64)
     else:
         part_file = None
-        part_chunk = np.unique(np.linspace(0, n, min(args.e2e_parts, max(1, n // 512)) + 1).astype(np.int64))
+        want = min(max(args.e2e_parts, int(U // (512 << 20))), max(1, n // 512))
+        part_chunk = np.unique(np.linspace(0, n, want + 1).astype(np.int64))
     nparts = len(part_chunk) - 1
-    max_raw = max(int(raw_off[part_chunk[i + 1]] - raw_off[part_chunk[i]]) for i in range(nparts))
+    part_b0 = np.array([int(raw_off[part_chunk[i]]) for i in range(nparts + 1)], dtype=np.int64)
+    max_raw = int(np.diff(part_b0).max())
     max_slot = max(int(slot_off[part_chunk[i + 1]] - slot_off[part_chunk[i]]) for i in range(nparts))
-    workers = []
-    for wi in range(W):
-        wctx = zwz_b200.Context(local_rank)
-        workers.append(dict(ctx=wctx, s=torch.cuda.Stream(),
-                            raw=torch.empty(max_raw + 64, dtype=torch.uint8, device="cuda"),
-                            slots=torch.empty(max_slot + 64, dtype=torch.uint8, device="cuda"),
-                            packed=torch.empty(max_slot + 64, dtype=torch.uint8, device="cuda"),
-                            back=torch.empty(max_raw + 64, dtype=torch.uint8, device="cuda")))
-    wlocal = threading.local()
+    # page-locked host windows. Generated-in-full shards: the whole shard. Periodic shards (c3 at 16 GiB, c5): a window of
+    # whole periods + one part, so that any part is contiguous in it (byte x of the shard == unit[x mod period]).
+    if sh.periodic:
+        wrap = sh.period * max(1, (4 << 30) // sh.period)
+        win = wrap + max_raw
+    else:
+        wrap, win = None, U
+    h_raw = torch.empty(win, dtype=torch.uint8, pin_memory=True)
+    hr = h_raw.numpy()
+    if sh.periodic:
+        for o in range(0, win, sh.period):
+            k = min(sh.period, win - o)
+            hr[o:o + k] = sh.unit[:k]
+    else:
+        hr[:] = sh.unit
+    # outputs: the whole shard when it is generated in full; one region per worker when it is periodic (16 GiB would not fit)
+    back_stride = (max_raw + 4095) & ~4095
+    comp_stride = (max_slot + 64 + 4095) & ~4095
+    h_back = torch.empty(back_stride * W if sh.periodic else U, dtype=torch.uint8, pin_memory=True)
+    h_comp = torch.empty(comp_stride * W if sh.periodic else int(slot_off[-1]) + 64, dtype=torch.uint8, pin_memory=True)
+    last_part = [None] * W
+    hc_ptr, hr_ptr, hb_ptr = h_comp.data_ptr(), h_raw.data_ptr(), h_back.data_ptr()
+    workers = [zwz_b200.Context(local_rank) for _ in range(W)]
     wlock = threading.Lock()
     wfree = list(range(W))
     comp_bytes = [0] * nparts
+    part_desc = part_descriptors(sh, coff, clen, cfile, raw_off, slot_off, part_chunk, part_file, wrap)
 
     def e2e_part(i):
         with wlock:
             wi = wfree.pop()
         try:
-            w = workers[wi]
-            c0, c1 = int(part_chunk[i]), int(part_chunk[i + 1])
-            b0, b1 = int(raw_off[c0]), int(raw_off[c1])
-            so0 = slot_off[c0]
-            with torch.cuda.stream(w["s"]):
-                sp = w["s"].cuda_stream
-                w["raw"][:b1 - b0].copy_(h_raw[b0:b1], non_blocking=True)
-                pc = coff[c0:c1] - np.uint64(b0)
-                res = w["ctx"].deflate_batch_device(w["raw"].data_ptr(), pc, clen[c0:c1], w["slots"].data_ptr(), slot_off[c0:c1] - so0, args.level, sp)
-                if do_md5:
-                    f0, f1 = int(part_file[i]), int(part_file[i + 1])
-                    dg1 = w["ctx"].md5_batch_device(w["raw"].data_ptr(), f_off[f0:f1] - np.uint64(b0), f_len[f0:f1], sp)
-                poff = w["ctx"].pack_streams_device(w["slots"].data_ptr(), slot_off[c0:c1] - so0, res, w["packed"].data_ptr(), sp)
-                C = int(poff[-1])
-                hc0 = int(so0)
-                h_comp[hc0:hc0 + C].copy_(w["packed"][:C], non_blocking=True)   # payloads -> host (what a .zwz holds)
-                w["s"].synchronize()
-                w["packed"][:C].copy_(h_comp[hc0:hc0 + C], non_blocking=True)   # decompress side starts from host bytes
-                pr = np.concatenate([pc, [np.uint64(b1 - b0)]]).astype(np.uint64)
-                r_off, r_len, r_raw_off = records_of(res, poff, pr)
-                rl, st = w["ctx"].inflate_batch_device(w["packed"].data_ptr(), r_off, r_len, w["back"].data_ptr(), r_raw_off, 0, sp)
-                if do_md5:
-                    dg2 = w["ctx"].md5_batch_device(w["back"].data_ptr(), f_off[f0:f1] - np.uint64(b0), f_len[f0:f1], sp)
-                    assert np.array_equal(dg1, dg2)
-                h_back[b0:b1].copy_(w["back"][:b1 - b0], non_blocking=True)
-                w["s"].synchronize()
-            assert (st == 0).all()
-            comp_bytes[i] = C
+            d = part_desc[i]
+            cap = int(slot_off[d["c1"]] - slot_off[d["c0"]]) + 64
+            hc = wi * comp_stride if sh.periodic else d["hc"]
+            hb = wi * back_stride if sh.periodic else d["y0"]
+            comp_bytes[i] = host_roundtrip(workers[wi], d, clen, hr_ptr + d["y0"], hc_ptr + hc, cap, hb_ptr + hb, args.level, do_md5)
+            last_part[wi] = i
         finally:
             with wlock:
                 wfree.append(wi)
@@ -467,8 +658,8 @@ def main():
     Cbytes = int(res["len0"].sum() + res["len1"].sum())
     assert (state["st"] == 0).all(), "inflate status"
     assert (not do_md5) or np.array_equal(state["dg1"], state["dg2"]), "MD5 verify failed"
-    back = d_back[:U].cpu().numpy()
-    assert np.array_equal(back, buf), "round trip mismatch"
+    for o in range(0, U, 1 << 30):
+        assert torch.equal(d_back[o:min(U, o + (1 << 30))], d_raw[o:min(U, o + (1 << 30))]), "round trip mismatch"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -491,6 +682,7 @@ def main():
     for _ in range(2):
         e2e_step()
     barrier()
+    wl0 = sum(w.launches for w in workers)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
@@ -498,12 +690,20 @@ def main():
     e3.record()
     barrier()
     e2e_ms = e2.elapsed_time(e3)
+    e2e_launches = sum(w.launches for w in workers) - wl0
     clocks = sampler.stop()
-    assert np.array_equal(h_back.numpy(), buf), "e2e round trip mismatch"
+    if sh.periodic:   # what every worker wrote last
+        for wi, i in enumerate(last_part):
+            if i is not None:
+                d = part_desc[i]
+                k = d["b1"] - d["b0"]
+                assert np.array_equal(h_back.numpy()[wi * back_stride:wi * back_stride + k], hr[d["y0"]:d["y0"] + k]), "e2e round trip mismatch"
+    else:
+        assert np.array_equal(h_back.numpy(), hr), "e2e round trip mismatch"
 
     # max over ranks, totals over ranks (the ONLY collective: a few counters per GPU)
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([U, Cbytes, n, nf, launches], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([U, Cbytes, n, nf, launches + e2e_launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allc = [torch.zeros_like(cnt) for _ in range(world)]
@@ -511,25 +711,6 @@ def main():
         cnt = torch.stack(allc).sum(0)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     U_all, C_all, n_all, nf_all, launches_all = [float(x) for x in cnt]
-    # ---- the chunk-offset exchange: when ONE file is cut into contiguous chunk ranges over the
-    # GPUs, all its records must land in ONE archive (decompression.cpp:52-55), so every rank needs the byte offset at which
-    # its records start: record bytes per rank -> all-gather -> exclusive scan. 13 + path_len header bytes per record, +32 for
-    # the MD5 behind the file's last record. Sequence ids are offset the same way (records, not chunks: split chunks count twice).
-    exchange = None
-    if args.workload == "c3":
-        path_len = len("big/huge.log")
-        n_records = int(n + int((res["len1"] > 0).sum()))
-        rec_bytes = Cbytes + n_records * (13 + path_len) + (32 if rank == world - 1 else 0)
-        mine = torch.tensor([float(rec_bytes), float(n_records)], dtype=torch.float64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        if world > 1:
-            dist.all_gather(allv, mine)
-        else:
-            allv = [mine]
-        sizes_ = [int(v[0]) for v in allv]
-        recs_ = [int(v[1]) for v in allv]
-        exchange = {"rank_record_bytes": sizes_, "rank_write_offset": [int(sum(sizes_[:i])) for i in range(world)],
-                    "rank_first_sequence_id": [int(sum(recs_[:i])) for i in range(world)], "archive_bytes": int(sum(sizes_))}
 
     if rank == 0:
         K = args.steps
@@ -553,12 +734,16 @@ def main():
                 traffic = tj["kernels"].get(dom) * K / max(nl[dom], 1)   # per launch, like algorithmic_bytes_per_launch
         except Exception:
             pass
+        cfg = config_of(args, sh, world)
+        assert (cfg["chunks"], cfg["files"], cfg["uncompressed_bytes"]) == (int(n_all), int(nf_all), int(U_all)), "config totals"
         line = {
             "metric": METRIC, "value": U_all * K / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": desc, "e2e_pipeline": f"{W} workers x {nparts} parts, H2D/kernels/D2H overlapped", "step": ("deflate+MD5(src)+pack+inflate+MD5(out)" if do_md5 else "deflate+pack+inflate (no MD5: one file = one serial chain)") + ", all through the C ABI", "chunks": int(n_all),
-                       "files": int(nf_all), "uncompressed_bytes": int(U_all), "l2": "inputs (>= 2 GB/GPU) exceed the 126 MB L2",
-                       "level": args.level, "parallelism": f"files dealt size-descending round-robin over {world} GPU(s)"},
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": sh.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg,
+            "pipeline": {"step": ("deflate+MD5(src)+pack+inflate+MD5(out)" if do_md5 else "deflate+pack+inflate (no MD5: one file = one serial chain)") + ", all through the C ABI",
+                         "e2e": f"{W} worker contexts x {nparts} parts per rank through " +
+                                ("zwz_compress_files + zwz_decompress_records" if part_file is not None else "zwz_deflate_batch + zwz_inflate_batch") +
+                                " (host buffers in, host buffers out; the calls `main` makes)"},
             "ratio": U_all / C_all,
             "deflate_gbs": U * K / ((ms["lz_match"] + ms["deflate_encode"]) * 1e-3) / 1e9,
             "inflate_gbs": U * K / (ms["inflate"] * 1e-3) / 1e9,
@@ -570,12 +755,22 @@ def main():
             "e2e": {"value": U_all * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(U + state["C"]),
                     "d2h_bytes_per_step": int(U + state["C"]), "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches_all),
-            "zwz_offset_exchange": exchange,
             "clocks": clocks,
         }
+        # free the big buffers before the extra passes / CPU leg
+        if args.workload == "c2" and not args.no_extra and world == 1:
+            extra = {}
+            try:
+                s1 = build_shard("c1", 192 << 20, 0, 1)
+                extra["c1"] = device_pass(torch, zwz_b200, ctx, stream, s1, args.level, True, 3, 3)
+                s3 = build_shard("c3", 1 << 30, 0, 1)
+                extra["c3"] = device_pass(torch, zwz_b200, ctx, stream, s3, args.level, False, 3, 3)
+            except Exception as e:  # the headline line must not die on an extra
+                extra["error"] = repr(e)
+            line["extra_workloads"] = extra
         if not args.no_cpu_baseline:
             target = int(args.cpu_sample_mb * 1e6) if args.cpu_sample_mb else int(min(8e6 * cores, 400e6))
-            sb, so, what = sample_of(buf, foffs, target)
+            sb, so, what = sample_of(sh, target)
             scoff, sclen, _, _ = corpus.chunk_table(so)
             dt, comp, ok = cpu_step(sb, so, scoff, sclen, cores, do_md5)
             # our size on the very same sample, for the ratio criterion
@@ -587,6 +782,7 @@ def main():
             line["size_vs_zlib6"] = ours / max(comp, 1)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -80,6 +80,7 @@ def _declare(L):
     L.zwz_md5_hex.argtypes = [vp, vp]
     L.zwz_md5_hex.restype = None
     L.zwz_adler32_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp]
+    L.zwz_compress_files.argtypes = [vp, vp, vp, u32, i32, vp, u64, vp, vp, vp]
     L.zwz_decompress_records.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, vp, u64, vp, vp, vp, vp, u32]
     L.zwz_profile_enable.argtypes = [vp, i32]
     L.zwz_profile_read.argtypes = [vp, vp, vp, i32]
@@ -285,6 +286,58 @@ class Context:
         self._check(self.lib.zwz_decompress_records(self.h, _ptr(comp), _ptr(off), _ptr(length), _ptr(rec_cap), _ptr(rec_file), n, nf, _ptr(files),
                                                     out_cap, _ptr(foff), _ptr(rl), _ptr(st), _ptr(dg) if want_md5 else None, flags))
         return files, foff, rl, st, dg
+
+    # ---- the host-buffer calls with caller-owned (page-locked) buffers given by address: what host/compress_pipeline.cpp and
+    # host/decompress_pipeline.cpp do per batch; bench.py times these for its end-to-end number ----
+    def compress_files_into(self, data_ptr: int, file_off, level: int, out_ptr: int, out_cap: int, want_md5: bool = True):
+        """zwz_compress_files on raw addresses. file_off[nf+1] is relative to data_ptr. Returns (packed_off, results, digests)."""
+        file_off = np.ascontiguousarray(file_off, dtype=np.uint64)
+        nf = len(file_off) - 1
+        sizes = np.diff(file_off.astype(np.int64))
+        nc = int((sizes // CHUNK_SIZE + 1).sum())
+        poff = np.zeros(nc + 1, dtype=np.uint64)
+        res = np.zeros(nc, dtype=RESULT_DTYPE)
+        dg = np.zeros((nf, 16), dtype=np.uint8) if want_md5 else None
+        self._check(self.lib.zwz_compress_files(self.h, data_ptr, _ptr(file_off), nf, level, out_ptr, out_cap, poff.ctypes.data, _ptr(res),
+                                                _ptr(dg) if want_md5 else None))
+        return poff, res, dg
+
+    def decompress_records_into(self, comp_ptr: int, off, length, rec_cap, rec_file, nf: int, out_ptr: int, out_cap: int, want_md5: bool = True,
+                                flags: int = 0):
+        """zwz_decompress_records on raw addresses. Returns (file_off[nf+1], raw_len[n], status[n], digests)."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        rec_cap = np.ascontiguousarray(rec_cap, dtype=np.uint32)
+        rec_file = np.ascontiguousarray(rec_file, dtype=np.uint32)
+        n = len(off)
+        foff = np.zeros(nf + 1, dtype=np.uint64)
+        rl = np.zeros(n, dtype=np.uint32)
+        st = np.zeros(n, dtype=np.uint32)
+        dg = np.zeros((nf, 16), dtype=np.uint8) if want_md5 else None
+        self._check(self.lib.zwz_decompress_records(self.h, comp_ptr, _ptr(off), _ptr(length), _ptr(rec_cap), _ptr(rec_file), n, nf, out_ptr,
+                                                    out_cap, _ptr(foff), _ptr(rl), _ptr(st), _ptr(dg) if want_md5 else None, flags))
+        return foff, rl, st, dg
+
+    def deflate_batch_into(self, raw_ptr: int, off, length, out_ptr: int, out_cap: int, level: int = 0):
+        """zwz_deflate_batch on raw addresses. Returns (packed_off[n+1], results[n])."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        n = len(off)
+        poff = np.zeros(n + 1, dtype=np.uint64)
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        self._check(self.lib.zwz_deflate_batch(self.h, raw_ptr, _ptr(off), _ptr(length), n, out_ptr, out_cap, poff.ctypes.data, _ptr(res), level))
+        return poff, res
+
+    def inflate_batch_into(self, comp_ptr: int, off, length, out_ptr: int, raw_off, flags: int = 0):
+        """zwz_inflate_batch on raw addresses (raw_off[n+1] relative to out_ptr). Returns (raw_len[n], status[n])."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        raw_off = np.ascontiguousarray(raw_off, dtype=np.uint64)
+        n = len(off)
+        rl = np.zeros(n, dtype=np.uint32)
+        st = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.zwz_inflate_batch(self.h, comp_ptr, _ptr(off), _ptr(length), n, out_ptr, _ptr(raw_off), _ptr(rl), _ptr(st), flags))
+        return rl, st
 
     # ---- MD5: verification.cpp:13-27 ----
     def md5_batch(self, data, off, length) -> np.ndarray:

@@ -314,9 +314,8 @@ def c3_buffer(size: int = 16 << 30, seed: int = BASE_SEED, unit_bytes: int = 8 <
     return out
 
 
-def mixed_buffer(total_bytes: int, seed: int = BASE_SEED + 1, min_size: int = 4096, max_size: int = 16 << 20):
-    """C1/C5-shaped corpus as one buffer: files drawn from the C1 generator until `total_bytes` is reached.
-    Returns (bytes, offsets[n+1], specs)."""
+def mixed_specs(total_bytes: int, seed: int = BASE_SEED + 1, min_size: int = 4096, max_size: int = 16 << 20) -> List[FileSpec]:
+    """File list of a C1/C5-shaped corpus (no contents): files drawn from the C1 generator until `total_bytes` is reached."""
     specs: List[FileSpec] = []
     tot = 0
     batch = 0
@@ -329,6 +328,13 @@ def mixed_buffer(total_bytes: int, seed: int = BASE_SEED + 1, min_size: int = 40
             if tot >= total_bytes:
                 break
         batch += 1
+    return specs
+
+
+def mixed_buffer(total_bytes: int, seed: int = BASE_SEED + 1, min_size: int = 4096, max_size: int = 16 << 20):
+    """C1/C5-shaped corpus as one buffer: files drawn from the C1 generator until `total_bytes` is reached.
+    Returns (bytes, offsets[n+1], specs)."""
+    specs = mixed_specs(total_bytes, seed, min_size, max_size)
     offs = np.zeros(len(specs) + 1, dtype=np.int64)
     np.cumsum([s.size for s in specs], out=offs[1:])
     buf = np.empty(int(offs[-1]), dtype=np.uint8)
