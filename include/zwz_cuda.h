@@ -120,8 +120,10 @@ int zwz_pack_streams_device(zwz_ctx *ctx, const uint8_t *d_slots, const uint64_t
 /* Stream i is comp[off[i] .. off[i]+len[i]) (a complete RFC 1950 stream, or a truncated one). Output goes to
  * raw_out + raw_off[i] with capacity raw_off[i+1] - raw_off[i] (raw_off has n+1 entries). raw_len[i] = bytes produced —
  * exactly what zlib's inflate would have written for the same input (errors ignored as in decompression.cpp:31), or the
- * size needed when status[i] == ZWZ_STREAM_OUTPUT_FULL. flags: bit 0 = skip Adler-32 verification. */
+ * size needed when status[i] == ZWZ_STREAM_OUTPUT_FULL. flags: bit 0 = skip Adler-32 verification; bit 1 = decode with the
+ * careful (warp-redundant) decoder only, without the lane-parallel block decoder (same results; for A/B timing and tests). */
 #define ZWZ_INFLATE_NO_ADLER 1u
+#define ZWZ_INFLATE_CAREFUL 2u
 int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t *off, const uint32_t *len, uint32_t n,
                              uint8_t *d_raw_out, const uint64_t *raw_off, uint32_t *raw_len, uint32_t *status,
                              uint32_t flags, void *stream);
@@ -163,6 +165,26 @@ int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_o
 int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
                            const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
                            uint32_t *raw_len, uint32_t *status, uint8_t *digest /* nf*16 or NULL */, uint32_t flags);
+
+/* ---- asynchronous forms: the digests are DEFERRED ----------------------------------------------------------------------
+ * "asynchronous variants ... pair with a zwz_wait". A file's MD5 is one serial chain (~0.13 GB/s per file on
+ * one lane), so a batch holding a 16 MiB file would wait ~130 ms for its digests while its deflate/inflate kernels take a
+ * few milliseconds. The *_async calls return as soon as the BYTES are back in the caller's buffers (packed streams resp.
+ * decompressed files); the MD5 kernel keeps running on the context's second stream over the batch's device-resident copy
+ * and `digest` is filled in by zwz_wait(ticket). Two batches may be in flight per context; starting a third delivers the
+ * oldest one's digests first (its `digest` pointer must therefore stay valid until zwz_wait or until two more *_async calls
+ * on the context have returned). The host pipeline uses this to take MD5 off its batch critical path: records are
+ * serialised and archive offsets handed out while the digests are still being computed (compression.cpp:95-103 appends
+ * them behind the last record of a file; decompression.cpp:136-146 only needs them for the verdict line). */
+int zwz_compress_files_async(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                             uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest /* nf*16 or NULL */, uint64_t *ticket);
+int zwz_decompress_records_async(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                                 const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap,
+                                 uint64_t *file_off_out, uint32_t *raw_len, uint32_t *status, uint8_t *digest /* nf*16 or NULL */,
+                                 uint32_t flags, uint64_t *ticket);
+/* Blocks until the digests of `ticket` are in the buffer given to the *_async call (ticket 0 or an already delivered
+ * ticket: returns at once). */
+int zwz_wait(zwz_ctx *ctx, uint64_t ticket);
 
 /* ---- Adler-32 (the zlib trailer; exported for tests) ---------------------------------------------------------------- */
 int zwz_adler32_batch_device(zwz_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint32_t *len, uint32_t n,

@@ -47,7 +47,10 @@ struct InflateWarpSmem {
     uint32_t clt[128]; // code-length-code table (7 bits)
     uint16_t sorted_cl[20];
     uint32_t cnt_cl[16];
+    uint32_t cw[32u * 15u + 8u];  // inflate_fast.cuh: staged window of compressed words (ZWZ_IF_CW)
+    uint16_t tok[32u * 130u];     // inflate_fast.cuh: one token region per lane (32 x ZWZ_IF_RS)
 };
+#define ZWZ_INF_SMEM (ZWZ_INF_WARPS * (uint32_t) sizeof(zwz::InflateWarpSmem))
 
 ZWZ_DEV uint32_t inf_litlen_entry(uint32_t sym, uint32_t nb) {
     if (sym < 256u) return ZWZ_INF_ENTRY(nb, 0, INF_KIND_LIT, sym);
@@ -231,6 +234,15 @@ ZWZ_DEV void infb_drop(InfBits &b, uint32_t n) {
 }
 // bits consumed from the stream so far
 ZWZ_DEV uint64_t infb_used(const InfBits &b) { return b.fed - b.cnt; }
+// position the reader at stream bit `bit_pos`
+ZWZ_DEV void infb_seek_bits(InfBits &b, uint64_t bit_pos) {
+    infb_seek(b, (uint32_t) (bit_pos >> 3));
+    infb_drop(b, (uint32_t) bit_pos & 7u); // <= 7 of the >= 8 bits the seek left in the buffer
+}
+
+} // namespace zwz
+#include "inflate_fast.cuh"
+namespace zwz {
 
 // One warp decodes stream `sid`.
 ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp, uint32_t comp_len, uint8_t *out, uint32_t cap,
@@ -307,9 +319,9 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
             uint32_t avail = comp_len - bpos;
             uint32_t ncopy = len < avail ? len : avail;
             INF_FLUSH_LITS();
-            for (uint32_t i = lane; i < ncopy; i += 32u) {
-                uint32_t q = pos + i;
-                if (q < cap) out[q] = comp[bpos + i];
+            {
+                const uint32_t room = pos < cap ? cap - pos : 0u;
+                inf_copy_plain(out + pos, comp + bpos, ncopy < room ? ncopy : room);
             }
             if (pos + ncopy > cap) overflow = true;
             pos += ncopy;
@@ -432,6 +444,24 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
         }
 
         for (min_ll = 1; min_ll < 15u && S.cnt_ll[min_ll] == 0u; ++min_ll) {}
+        // ---- lane-parallel decode of the block (inflate_fast.cuh); the careful loop below only sees what it hands over:
+        // the first token that does not lie completely inside the input, or an invalid code ----
+        if (!(flags & ZWZ_INFLATE_CAREFUL)) {
+            INF_FLUSH_LITS();
+            __syncwarp();
+            uint64_t bp = infb_used(B);
+            const int fr = inf_fast_block(S, B, bp, max_ll, max_d, out, cap, pos, overflow);
+            pend_lo = pos;
+            if (fr == IFR_BAD) {
+                status = ZWZ_STREAM_BAD;
+                goto done;
+            }
+            infb_seek_bits(B, bp);
+            if (fr == IFR_EOB) {
+                if (last) break;
+                continue;
+            }
+        }
         // ---- symbol loop ----
         for (;;) {
             infb_refill(B); // >= 33 valid bits
@@ -558,23 +588,7 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
             INF_FLUSH_LITS();
             __syncwarp();
             if (pos + mlen > cap) overflow = true;
-            if (mlen <= 32u && dist >= mlen) { // the common case: short, non-overlapping — one step, no loop
-                const uint32_t q = pos + lane;
-                if (lane < mlen && q < cap) out[q] = __ldcg(out + (q - dist));
-            } else if (dist >= 32u || dist >= mlen) {
-                for (uint32_t base = 0; base < mlen; base += 32u) { // warp-uniform trip count
-                    uint32_t q = pos + base + lane;
-                    if (base + lane < mlen && q < cap) out[q] = __ldcg(out + (q - dist));
-                    __syncwarp(); // later steps may read what this step wrote (dist < mlen)
-                }
-            } else { // overlapping run with a period < 32: every byte comes from the already written period
-                const uint32_t src0 = pos - dist;
-                for (uint32_t i = lane; i < mlen; i += 32u) {
-                    uint32_t q = pos + i;
-                    if (q < cap) out[q] = __ldcg(out + (src0 + (i % dist)));
-                }
-            }
-            __syncwarp();
+            inf_copy_match(out, pos, mlen, dist, cap);
             pos += mlen;
             pend_lo = pos;
         }
@@ -592,28 +606,8 @@ ZWZ_DEV void inflate_stream(InflateWarpSmem &S, const uint8_t *__restrict__ comp
         }
         if (!(flags & 1u) && !overflow) {
             uint32_t want = ((uint32_t) comp[bpos] << 24) | ((uint32_t) comp[bpos + 1] << 16) | ((uint32_t) comp[bpos + 2] << 8) | comp[bpos + 3];
-            // a = 1 + sum(byte), b = n + sum((n - j) * byte_j)  (mod 65521)
-            uint64_t s0 = 0, s1 = 0;
-            if (pos < 131042u) { // j mod 65521 is one conditional subtract (every record the reference writes is here)
-                for (uint32_t j = lane; j < pos; j += 32u) {
-                    uint32_t v = ((volatile uint8_t *) out)[j];
-                    uint32_t jm = j >= 65521u ? j - 65521u : j;
-                    s0 += v;
-                    s1 += (uint64_t) jm * v;
-                }
-            } else {
-                for (uint32_t j = lane; j < pos; j += 32u) {
-                    uint32_t v = ((volatile uint8_t *) out)[j];
-                    s0 += v;
-                    s1 += (uint64_t) (j % 65521u) * v;
-                }
-            }
-            s0 = warp_sum64(s0) % 65521u;
-            s1 = warp_sum64(s1 % 65521u) % 65521u;
-            uint64_t nm = pos % 65521u;
-            uint32_t a = (uint32_t) ((1u + s0) % 65521u);
-            uint32_t bsum = (uint32_t) ((nm + nm * s0 + 65521u - s1) % 65521u);
-            if (((bsum << 16) | a) != want) status = ZWZ_STREAM_BAD;
+            const uint32_t have = inf_adler32(out, pos); // a = 1 + sum(byte), b = n + sum((n - j) * byte_j)  (mod 65521)
+            if (have != want) status = ZWZ_STREAM_BAD;
         }
     }
 done:
@@ -632,7 +626,8 @@ ZWZ_KERNEL __launch_bounds__(ZWZ_INF_WARPS * 32) inflate_kernel(const uint8_t *_
                                                               const uint32_t *__restrict__ len, uint8_t *raw_out,
                                                               const uint64_t *__restrict__ raw_off, uint32_t *raw_len, uint32_t *status,
                                                               uint32_t n, uint32_t flags, uint32_t *work_counter) {
-    __shared__ InflateWarpSmem smem[ZWZ_INF_WARPS];
+    ZWZ_DYN_SMEM(inf_raw);
+    InflateWarpSmem *smem = (InflateWarpSmem *) inf_raw;
     for (;;) {
         uint32_t sid = 0;
         if (lane_id() == 0) sid = atomicAdd(work_counter, 1u);

@@ -71,6 +71,21 @@ struct Arena {
     bool pinned = false;
 };
 
+// Deferred MD5 of one host-buffer batch (zwz_compress_files_async / zwz_decompress_records_async): the bytes to hash stay
+// resident in `data` while the digests are computed on the context's second stream; the caller collects them with zwz_wait.
+// Two slots per context, used alternately: the MD5 of batch k runs while batch k+1 goes through the main stream.
+struct DigestSlot {
+    Arena data;   // device: compress side = the raw files of the batch; decompress side = the concatenated output files
+    Arena meta;   // device: MD5 descriptors + digests
+    Arena pin;    // page-locked: descriptors (upload source) + digests (download target)
+    zwz_rt::zwz_sync_event_t ev_in{}, ev_done{};
+    bool pending = false;
+    uint32_t n = 0;
+    size_t digest_off = 0;     // where the digests land inside `pin`
+    uint8_t *digest_dst = nullptr;
+    uint64_t ticket = 0;
+};
+
 } // namespace zwz
 
 struct zwz_ctx {
@@ -78,10 +93,14 @@ struct zwz_ctx {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t total_mem = 0, smem_optin = 0;
     zwz_stream_t stream = nullptr;
+    zwz_stream_t md5_stream = nullptr; // deferred digests (DigestSlot)
+    zwz::DigestSlot slot[2];
+    int next_slot = 0;
+    uint64_t ticket_seq = 0;
     std::string err;
     uint64_t launches = 0;
     zwz::Arena meta, scratch, bulk_in, bulk_out, packed, pin_meta, pin_aux, counter;
-    int inflate_mode = 0; // 0/1 = one warp per stream, 2 = one lane per stream (ZWZ_INFLATE_MODE=warp|lanes)
+    int inflate_mode = 0; // 0/1 = one warp per stream, 2 = one lane per stream, 3 = one warp per stream without the lane-parallel block decoder (ZWZ_INFLATE_MODE=warp|lanes|careful)
     bool arena_async = true; // ZWZ_ARENA_SYNC=1: plain cudaMalloc/cudaFree arenas (for A/B timing)
     bool trace = false;   // ZWZ_TRACE=1: wall-clock phases of the host-buffer calls on stderr (syncs the stream at every mark)
     size_t batch_raw_bytes = (size_t) 4 << 30; // raw bytes per internal deflate sub-batch (scratch = 6x that; ZWZ_BATCH_RAW_MB overrides)
@@ -235,10 +254,20 @@ int zwz_init(int device, zwz_ctx **out) {
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<2>, zwz::MatchClass<2>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::lz_match_kernel<3>, zwz::MatchClass<3>::kSmem) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::md5_files_staged_kernel, ZWZ_MD5S_SMEM) ||
+        zwz_rt::set_max_dyn_smem((const void *) zwz::inflate_kernel, ZWZ_INF_SMEM) ||
         zwz_rt::set_max_dyn_smem((const void *) zwz::inflate_lanes_kernel, ZWZ_IL_SMEM)) {
         delete ctx;
         return ZWZ_E_NODEVICE;
     }
+    if (zwz_rt::stream_create(&ctx->md5_stream)) {
+        delete ctx;
+        return ZWZ_E_NODEVICE;
+    }
+    for (auto &sl : ctx->slot)
+        if (zwz_rt::sync_event_create(&sl.ev_in) || zwz_rt::sync_event_create(&sl.ev_done)) {
+            delete ctx;
+            return ZWZ_E_NODEVICE;
+        }
     zwz_rt::keep_pool_memory(device);
     zwz_rt::preload_kernel((const void *) zwz::deflate_encode_kernel);
     zwz_rt::preload_kernel((const void *) zwz::inflate_kernel);
@@ -248,7 +277,7 @@ int zwz_init(int device, zwz_ctx **out) {
     zwz_rt::preload_kernel((const void *) zwz::adler32_kernel);
     if (const char *e = getenv("ZWZ_ARENA_SYNC")) ctx->arena_async = !(*e && *e != '0');
     if (const char *e = getenv("ZWZ_TRACE")) ctx->trace = *e && *e != '0';
-    if (const char *e = getenv("ZWZ_INFLATE_MODE")) ctx->inflate_mode = !strcmp(e, "warp") ? 1 : (!strcmp(e, "lanes") ? 2 : 0);
+    if (const char *e = getenv("ZWZ_INFLATE_MODE")) ctx->inflate_mode = !strcmp(e, "warp") ? 1 : (!strcmp(e, "lanes") ? 2 : (!strcmp(e, "careful") ? 3 : 0));
     if (const char *e = getenv("ZWZ_BATCH_RAW_MB")) {
         long v = atol(e);
         if (v >= 1) ctx->batch_raw_bytes = (size_t) v << 20;
@@ -261,6 +290,14 @@ void zwz_destroy(zwz_ctx *ctx) {
     if (!ctx) return;
     zwz_rt::set_device(ctx->device);
     zwz_rt::stream_sync(ctx->stream);
+    zwz_rt::stream_sync(ctx->md5_stream);
+    for (auto &sl : ctx->slot) {
+        release(ctx, sl.data);
+        release(ctx, sl.meta);
+        release(ctx, sl.pin);
+        zwz_rt::sync_event_destroy(sl.ev_in);
+        zwz_rt::sync_event_destroy(sl.ev_done);
+    }
     release(ctx, ctx->meta);
     release(ctx, ctx->scratch);
     release(ctx, ctx->bulk_in);
@@ -271,6 +308,7 @@ void zwz_destroy(zwz_ctx *ctx) {
     release(ctx, ctx->counter);
     zwz_rt::stream_sync(ctx->stream);
     zwz_rt::stream_destroy(ctx->stream);
+    zwz_rt::stream_destroy(ctx->md5_stream);
     delete ctx;
 }
 
@@ -497,11 +535,15 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
 
 static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
                       uint32_t n, uint8_t *digest, int finalize, void *stream_v);
+static int slot_finish(zwz_ctx *ctx, zwz::DigestSlot &sl);
+static int slot_acquire(zwz_ctx *ctx, zwz::DigestSlot **out);
+static int slot_queue_md5(zwz_ctx *ctx, zwz::DigestSlot &sl, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *digest, uint64_t *ticket);
 
 static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
                              uint64_t *packed_off, zwz_deflate_result *res, int level, const uint64_t *md5_off, const uint64_t *md5_len,
-                             uint32_t md5_n, uint8_t *digest) {
+                             uint32_t md5_n, uint8_t *digest, uint64_t *ticket) {
     if (!ctx) return ZWZ_E_ARG;
+    if (ticket) *ticket = 0;
     if (!packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
     packed_off[0] = 0;
     if (n == 0) return ZWZ_OK;
@@ -523,17 +565,27 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
     }
     int rc;
     Trace tr(ctx, "compress");
-    if ((rc = reserve(ctx, ctx->bulk_in, (size_t) (hi - lo) + 64, false))) return rc;
+    // the raw bytes live in a digest slot: their MD5 runs on the second stream and may outlive this call (ticket != NULL)
+    zwz::DigestSlot *sl = nullptr;
+    if ((rc = slot_acquire(ctx, &sl))) return rc;
+    if ((rc = reserve(ctx, sl->data, (size_t) (hi - lo) + 64, false))) return rc;
     if ((rc = reserve(ctx, ctx->bulk_out, (size_t) slot[n] + 64, false))) return rc;
     tr.mark("reserve");
-    if (zwz_rt::memcpy_h2d(ctx->bulk_in.p, raw + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "raw upload failed");
+    if (zwz_rt::memcpy_h2d(sl->data.p, raw + lo, (size_t) (hi - lo), ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "raw upload failed");
     tr.mark("h2d");
-    if (digest && md5_n) { // MD5 of the source files from the same resident copy (no second upload)
+    if (digest && md5_n) { // MD5 of the source files from the same resident copy (no second upload), beside the deflate kernels
         std::vector<uint64_t> mo(md5_n);
         for (uint32_t i = 0; i < md5_n; ++i) mo[i] = md5_off[i] - lo;
-        if ((rc = md5_launch(ctx, nullptr, (const uint8_t *) ctx->bulk_in.p, mo.data(), md5_len, nullptr, md5_n, digest, 1, nullptr))) return rc;
+        if ((rc = slot_queue_md5(ctx, *sl, mo.data(), md5_len, md5_n, digest, ticket))) return rc;
     }
-    if ((rc = zwz_deflate_batch_device(ctx, (const uint8_t *) ctx->bulk_in.p, roff.data(), len, n, (uint8_t *) ctx->bulk_out.p, slot.data(), res,
+    struct Disarm { // an error below must not leave a pointer into the caller's memory behind in the slot
+        zwz::DigestSlot *s;
+        bool ok = false;
+        ~Disarm() {
+            if (!ok) s->digest_dst = nullptr;
+        }
+    } disarm{sl};
+    if ((rc = zwz_deflate_batch_device(ctx, (const uint8_t *) sl->data.p, roff.data(), len, n, (uint8_t *) ctx->bulk_out.p, slot.data(), res,
                                        level, nullptr)))
         return rc;
     tr.mark("md5+deflate");
@@ -561,6 +613,9 @@ static int deflate_host_impl(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *o
     tr.mark("pack");
     if (zwz_rt::memcpy_d2h(out, d_packed, (size_t) packed_off[n], ctx->stream) || zwz_rt::stream_sync(ctx->stream))
         return fail(ctx, ZWZ_E_CUDA, "compressed download failed");
+    tr.mark("d2h");
+    disarm.ok = true;
+    if (!ticket) return slot_finish(ctx, *sl); // synchronous form: the digests are part of the result
     return ZWZ_OK;
 }
 
@@ -596,7 +651,7 @@ int zwz_pack_streams_device(zwz_ctx *ctx, const uint8_t *d_slots, const uint64_t
 
 int zwz_deflate_batch(zwz_ctx *ctx, const uint8_t *raw, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *out, uint64_t out_cap,
                       uint64_t *packed_off, zwz_deflate_result *res, int level) {
-    return deflate_host_impl(ctx, raw, off, len, n, out, out_cap, packed_off, res, level, nullptr, nullptr, 0, nullptr);
+    return deflate_host_impl(ctx, raw, off, len, n, out, out_cap, packed_off, res, level, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 uint64_t zwz_count_chunks(const uint64_t *file_off, uint32_t nf) {
@@ -605,8 +660,8 @@ uint64_t zwz_count_chunks(const uint64_t *file_off, uint32_t nf) {
     return c;
 }
 
-int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
-                       uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest) {
+static int compress_files_impl(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                               uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest, uint64_t *ticket) {
     if (!ctx) return ZWZ_E_ARG;
     if (!file_off || !packed_off) return fail(ctx, ZWZ_E_ARG, "null argument");
     uint64_t nc = zwz_count_chunks(file_off, nf);
@@ -626,7 +681,27 @@ int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_o
         }
     }
     return deflate_host_impl(ctx, data, coff.data(), clen.data(), (uint32_t) nc, out, out_cap, packed_off, res, level, file_off, flen.data(),
-                             digest ? nf : 0, digest);
+                             digest ? nf : 0, digest, ticket);
+}
+
+int zwz_compress_files(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                       uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest) {
+    return compress_files_impl(ctx, data, file_off, nf, level, out, out_cap, packed_off, res, digest, nullptr);
+}
+
+int zwz_compress_files_async(zwz_ctx *ctx, const uint8_t *data, const uint64_t *file_off, uint32_t nf, int level, uint8_t *out, uint64_t out_cap,
+                             uint64_t *packed_off, zwz_deflate_result *res, uint8_t *digest, uint64_t *ticket) {
+    if (!ticket) return ctx ? fail(ctx, ZWZ_E_ARG, "null ticket") : ZWZ_E_ARG;
+    return compress_files_impl(ctx, data, file_off, nf, level, out, out_cap, packed_off, res, digest, ticket);
+}
+
+int zwz_wait(zwz_ctx *ctx, uint64_t ticket) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (ticket == 0) return ZWZ_OK;
+    zwz_rt::set_device(ctx->device);
+    for (auto &sl : ctx->slot)
+        if (sl.pending && sl.ticket == ticket) return slot_finish(ctx, sl);
+    return ZWZ_OK; // already delivered (a later batch needed the slot)
 }
 
 // ======================================================================================================================
@@ -681,8 +756,10 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
                        (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat,
                        (const uint32_t *) (dm + m_order), n, flags, d_counter);
         } else {
-            uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * 8u);
-            ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, 0, st, d_comp, (const uint64_t *) (dm + m_off),
+            const uint32_t per_sm = std::max<uint32_t>(1u, (uint32_t) ((228u * 1024u) / (ZWZ_INF_SMEM + 1024u)));
+            uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * per_sm);
+            if (ctx->inflate_mode == 3) flags |= ZWZ_INFLATE_CAREFUL;
+            ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, ZWZ_INF_SMEM, st, d_comp, (const uint64_t *) (dm + m_off),
                        (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat, n, flags, d_counter);
         }
     }
@@ -720,10 +797,11 @@ int zwz_inflate_batch(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, co
     return ZWZ_OK;
 }
 
-int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
-                           const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
-                           uint32_t *raw_len, uint32_t *status, uint8_t *digest, uint32_t flags) {
+static int decompress_records_impl(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                                   const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
+                                   uint32_t *raw_len, uint32_t *status, uint8_t *digest, uint32_t flags, uint64_t *ticket) {
     if (!ctx) return ZWZ_E_ARG;
+    if (ticket) *ticket = 0;
     if (!file_off_out) return fail(ctx, ZWZ_E_ARG, "null argument");
     for (uint32_t f = 0; f <= nf; ++f) file_off_out[f] = 0;
     if (n == 0) {
@@ -787,8 +865,12 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     while (f < nf) file_off_out[++f] = acc;
     if (acc > out_cap) return fail(ctx, ZWZ_E_CAPACITY, "output buffer too small");
     const size_t m_dst = (size_t) n * 8, m_len = 2 * (size_t) n * 8, meta_bytes = m_len + (size_t) n * 4;
-    if ((rc = reserve(ctx, ctx->packed, (size_t) acc + align_up(meta_bytes, 256) + 256, false))) return rc;
-    // NOT pin_meta: md5_launch below refills pin_meta while this upload may still be in flight (page-locked memory is read by
+    // the concatenated files live in a digest slot: their MD5 runs on the second stream and may outlive this call
+    zwz::DigestSlot *sl = nullptr;
+    if ((rc = slot_acquire(ctx, &sl))) return rc;
+    if ((rc = reserve(ctx, sl->data, (size_t) acc + 256, false))) return rc;
+    if ((rc = reserve(ctx, ctx->packed, align_up(meta_bytes, 256) + 256, false))) return rc;
+    // NOT pin_meta: other calls refill pin_meta while this upload may still be in flight (page-locked memory is read by
     // the DMA engine after cudaMemcpyAsync returns) — a reuse race that corrupted gather descriptors once per ~10^5 records.
     if ((rc = reserve(ctx, ctx->pin_aux, meta_bytes, true))) return rc;
     tr.mark("reserve2");
@@ -797,7 +879,7 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     memcpy(hp + m_dst, dst.data(), (size_t) n * 8);
     memcpy(hp + m_len, raw_len, (size_t) n * 4);
     uint8_t *dmeta = (uint8_t *) ctx->packed.p;
-    uint8_t *d_files = dmeta + align_up(meta_bytes, 256);
+    uint8_t *d_files = (uint8_t *) sl->data.p;
     if (zwz_rt::memcpy_h2d(dmeta, hp, meta_bytes, ctx->stream)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     {
         ProfSpan ps(ctx, ZWZ_PROF_PACK, ctx->stream);
@@ -806,42 +888,57 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
     }
     if ((rc = check_launch(ctx, "gather_records_kernel"))) return rc;
     tr.mark("gather");
-    if (digest && nf) {
+    if (digest && nf) { // beside the download of the files
         std::vector<uint64_t> fo(nf), fl(nf);
         for (uint32_t i = 0; i < nf; ++i) {
             fo[i] = file_off_out[i];
             fl[i] = file_off_out[i + 1] - file_off_out[i];
         }
-        if ((rc = md5_launch(ctx, nullptr, d_files, fo.data(), fl.data(), nullptr, nf, digest, 1, nullptr))) return rc;
+        if ((rc = slot_queue_md5(ctx, *sl, fo.data(), fl.data(), nf, digest, ticket))) return rc;
     }
-    tr.mark("md5");
-    if (zwz_rt::memcpy_d2h(files_out, d_files, (size_t) acc, ctx->stream) || zwz_rt::stream_sync(ctx->stream))
+    tr.mark("md5 queued");
+    if (zwz_rt::memcpy_d2h(files_out, d_files, (size_t) acc, ctx->stream) || zwz_rt::stream_sync(ctx->stream)) {
+        sl->digest_dst = nullptr;
         return fail(ctx, ZWZ_E_CUDA, "raw download failed");
+    }
     tr.mark("d2h");
+    if (!ticket) return slot_finish(ctx, *sl);
     return ZWZ_OK;
+}
+
+int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                           const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
+                           uint32_t *raw_len, uint32_t *status, uint8_t *digest, uint32_t flags) {
+    return decompress_records_impl(ctx, comp, off, len, rec_cap, rec_file, n, nf, files_out, out_cap, file_off_out, raw_len, status, digest, flags,
+                                   nullptr);
+}
+
+int zwz_decompress_records_async(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *off, const uint32_t *len, const uint32_t *rec_cap,
+                                 const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
+                                 uint32_t *raw_len, uint32_t *status, uint8_t *digest, uint32_t flags, uint64_t *ticket) {
+    if (!ticket) return ctx ? fail(ctx, ZWZ_E_ARG, "null ticket") : ZWZ_E_ARG;
+    return decompress_records_impl(ctx, comp, off, len, rec_cap, rec_file, n, nf, files_out, out_cap, file_off_out, raw_len, status, digest, flags,
+                                   ticket);
 }
 
 // ======================================================================================================================
 // MD5 / Adler-32
 // ======================================================================================================================
-static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
-                      uint32_t n, uint8_t *digest, int finalize, void *stream_v) {
-    if (!ctx) return ZWZ_E_ARG;
-    if (n == 0) return ZWZ_OK;
-    if (!off || !len || (finalize && !digest)) return fail(ctx, ZWZ_E_ARG, "null argument");
-    zwz_rt::set_device(ctx->device);
-    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+// Queues the MD5 kernel over n files on `st`: descriptors go up from `pin`, digests (and chained states) come back into `pin`
+// at *digest_off (resp. m_state). Nothing is waited for.
+static int md5_enqueue(zwz_ctx *ctx, zwz_stream_t st, Arena &dev_meta, Arena &pin, uint32_t *state, const uint8_t *d_data, const uint64_t *off,
+                       const uint64_t *len, const uint64_t *total_len, uint32_t n, int finalize, size_t *digest_off) {
     const size_t m_len = (size_t) n * 8, m_tot = 2 * (size_t) n * 8, m_state = 3 * (size_t) n * 8, meta_bytes = m_state + (size_t) n * 16;
     const size_t r_base = align_up(meta_bytes, 256);
     int rc;
-    if ((rc = reserve(ctx, ctx->pin_meta, meta_bytes, true))) return rc;
-    if ((rc = reserve(ctx, ctx->meta, r_base + (size_t) n * 16 + 256, false))) return rc;
-    uint8_t *hp = (uint8_t *) ctx->pin_meta.p;
+    if ((rc = reserve(ctx, pin, r_base + (size_t) n * 16, true))) return rc;
+    if ((rc = reserve(ctx, dev_meta, r_base + (size_t) n * 16 + 256, false))) return rc;
+    uint8_t *hp = (uint8_t *) pin.p;
     memcpy(hp, off, (size_t) n * 8);
     memcpy(hp + m_len, len, (size_t) n * 8);
     if (total_len) memcpy(hp + m_tot, total_len, (size_t) n * 8);
     if (state) memcpy(hp + m_state, state, (size_t) n * 16);
-    uint8_t *dm = (uint8_t *) ctx->meta.p;
+    uint8_t *dm = (uint8_t *) dev_meta.p;
     if (zwz_rt::memcpy_h2d(dm, hp, meta_bytes, st)) return fail(ctx, ZWZ_E_CUDA, "descriptor upload failed");
     uint8_t *d_digest = dm + r_base;
     {
@@ -861,11 +958,57 @@ static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, cons
         }
     }
     if ((rc = check_launch(ctx, "md5_files_kernel"))) return rc;
-    if (finalize && zwz_rt::memcpy_d2h(hp, d_digest, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "digest download failed");
+    if (finalize && zwz_rt::memcpy_d2h(hp + r_base, d_digest, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "digest download failed");
     if (state && zwz_rt::memcpy_d2h(hp + m_state, dm + m_state, (size_t) n * 16, st)) return fail(ctx, ZWZ_E_CUDA, "state download failed");
+    *digest_off = r_base;
+    return ZWZ_OK;
+}
+
+static int md5_launch(zwz_ctx *ctx, uint32_t *state, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, const uint64_t *total_len,
+                      uint32_t n, uint8_t *digest, int finalize, void *stream_v) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (n == 0) return ZWZ_OK;
+    if (!off || !len || (finalize && !digest)) return fail(ctx, ZWZ_E_ARG, "null argument");
+    zwz_rt::set_device(ctx->device);
+    zwz_stream_t st = stream_v ? (zwz_stream_t) stream_v : ctx->stream;
+    size_t doff = 0;
+    int rc = md5_enqueue(ctx, st, ctx->meta, ctx->pin_meta, state, d_data, off, len, total_len, n, finalize, &doff);
+    if (rc) return rc;
     if (zwz_rt::stream_sync(st)) return fail(ctx, ZWZ_E_CUDA, "md5 kernel failed");
-    if (finalize) memcpy(digest, hp, (size_t) n * 16);
-    if (state) memcpy(state, hp + m_state, (size_t) n * 16);
+    const uint8_t *hp = (const uint8_t *) ctx->pin_meta.p;
+    if (finalize) memcpy(digest, hp + doff, (size_t) n * 16);
+    if (state) memcpy(state, hp + 3 * (size_t) n * 8, (size_t) n * 16);
+    return ZWZ_OK;
+}
+
+// ---- deferred digests (DigestSlot) ---------------------------------------------------------------------------------
+// the slot a new batch may use: its previous batch's digests are delivered first if nobody has waited for them yet
+static int slot_finish(zwz_ctx *ctx, zwz::DigestSlot &sl) {
+    if (!sl.pending) return ZWZ_OK;
+    sl.pending = false;
+    if (zwz_rt::sync_event_wait(sl.ev_done)) return fail(ctx, ZWZ_E_CUDA, "md5 kernel failed");
+    if (sl.digest_dst && sl.n) memcpy(sl.digest_dst, (const uint8_t *) sl.pin.p + sl.digest_off, (size_t) sl.n * 16);
+    return ZWZ_OK;
+}
+static int slot_acquire(zwz_ctx *ctx, zwz::DigestSlot **out) {
+    zwz::DigestSlot &sl = ctx->slot[ctx->next_slot];
+    ctx->next_slot ^= 1;
+    int rc = slot_finish(ctx, sl);
+    *out = &sl;
+    return rc;
+}
+// MD5 of n files inside sl.data, queued on the second stream behind everything the main stream has queued so far
+static int slot_queue_md5(zwz_ctx *ctx, zwz::DigestSlot &sl, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *digest, uint64_t *ticket) {
+    if (zwz_rt::sync_event_record(sl.ev_in, ctx->stream) || zwz_rt::stream_wait_event(ctx->md5_stream, sl.ev_in))
+        return fail(ctx, ZWZ_E_CUDA, "stream dependency failed");
+    int rc = md5_enqueue(ctx, ctx->md5_stream, sl.meta, sl.pin, nullptr, (const uint8_t *) sl.data.p, off, len, nullptr, n, 1, &sl.digest_off);
+    if (rc) return rc;
+    if (zwz_rt::sync_event_record(sl.ev_done, ctx->md5_stream)) return fail(ctx, ZWZ_E_CUDA, "event record failed");
+    sl.pending = true;
+    sl.n = n;
+    sl.digest_dst = digest;
+    sl.ticket = ++ctx->ticket_seq;
+    if (ticket) *ticket = sl.ticket;
     return ZWZ_OK;
 }
 

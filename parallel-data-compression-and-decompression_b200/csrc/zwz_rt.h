@@ -45,6 +45,12 @@ inline int memcpy_d2h(void *d, const void *s, size_t n, zwz_stream_t) { if (n) m
 inline int memset_device(void *d, int v, size_t n, zwz_stream_t) { if (n) memset(d, v, n); return 0; }
 inline int last_error(std::string &) { return 0; }
 inline int set_max_dyn_smem(const void *, size_t) { return 0; }
+typedef int zwz_sync_event_t; // ordering-only events: the emulator runs everything in call order
+inline int sync_event_create(zwz_sync_event_t *e) { *e = 0; return 0; }
+inline int sync_event_destroy(zwz_sync_event_t) { return 0; }
+inline int sync_event_record(zwz_sync_event_t, zwz_stream_t) { return 0; }
+inline int sync_event_wait(zwz_sync_event_t) { return 0; }
+inline int stream_wait_event(zwz_stream_t, zwz_sync_event_t) { return 0; }
 typedef double zwz_event_t; // wall-clock stamp
 inline int event_record(zwz_event_t *e, zwz_stream_t) {
     struct timespec ts;
@@ -121,6 +127,13 @@ inline int last_error(std::string &msg) {
 inline int set_max_dyn_smem(const void *fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) == cudaSuccess ? 0 : 1;
 }
+// ordering-only events (no timing): cross-stream dependencies and the completion of deferred work (zwz_wait)
+typedef cudaEvent_t zwz_sync_event_t;
+inline int sync_event_create(zwz_sync_event_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess ? 0 : 1; }
+inline int sync_event_destroy(zwz_sync_event_t e) { return cudaEventDestroy(e) == cudaSuccess ? 0 : 1; }
+inline int sync_event_record(zwz_sync_event_t e, zwz_stream_t st) { return cudaEventRecord(e, st) == cudaSuccess ? 0 : 1; }
+inline int sync_event_wait(zwz_sync_event_t e) { return cudaEventSynchronize(e) == cudaSuccess ? 0 : 1; }
+inline int stream_wait_event(zwz_stream_t st, zwz_sync_event_t e) { return cudaStreamWaitEvent(st, e, 0) == cudaSuccess ? 0 : 1; }
 typedef cudaEvent_t zwz_event_t;
 inline int event_record(zwz_event_t *e, zwz_stream_t st) {
     if (cudaEventCreate(e) != cudaSuccess) return 1;

@@ -72,6 +72,21 @@ def cuda_ctx_warp():
 
 
 @pytest.fixture(scope="session")
+def cuda_ctx_careful():
+    ctx = _with_mode(_cuda_context, "careful")
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
+def emu_ctx_careful():
+    import emu_lib
+    ctx = _with_mode(emu_lib.emu_context, "careful")
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
 def emu_ctx_lanes():
     import emu_lib
     ctx = _with_mode(emu_lib.emu_context, "lanes")
@@ -79,10 +94,13 @@ def emu_ctx_lanes():
     ctx.close()
 
 
-# The two inflate mappings (one warp per stream / one lane per stream) are picked by batch size in production; the inflate
-# tests force each of them on the same inputs.
-INFLATE_BACKENDS = [pytest.param("emu_ctx", id="emu-warp"), pytest.param("emu_ctx_lanes", id="emu-lanes"),
+# The inflate decoders: one warp per stream with the lane-parallel block decoder (the product default: inflate_fast.cuh inside
+# inflate.cuh), the same without it ("careful": every symbol decoded warp-redundantly — also what the default hands
+# truncated/invalid streams to), and one lane per stream (inflate_lanes.cuh). The inflate tests run all three on the same inputs.
+INFLATE_BACKENDS = [pytest.param("emu_ctx", id="emu-warp"), pytest.param("emu_ctx_careful", id="emu-careful"),
+                    pytest.param("emu_ctx_lanes", id="emu-lanes"),
                     pytest.param("cuda_ctx_warp", id="cuda-warp", marks=pytest.mark.gpu),
+                    pytest.param("cuda_ctx_careful", id="cuda-careful", marks=pytest.mark.gpu),
                     pytest.param("cuda_ctx_lanes", id="cuda-lanes", marks=pytest.mark.gpu)]
 
 
