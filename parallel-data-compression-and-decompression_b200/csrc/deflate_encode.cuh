@@ -48,6 +48,7 @@ struct EncWarpSmem {
     uint8_t cl_ext[320];
     uint32_t stage[64];     // bit sink staging window
     uint32_t misc[8];
+    uint32_t region[16];    // stored regions of the chunk: token ranges [region[2i], region[2i+1])
 };
 #define ZWZ_DE_SMEM (ZWZ_DE_WARPS * (uint32_t) sizeof(zwz::EncWarpSmem))
 
@@ -549,6 +550,119 @@ ZWZ_DEV_NOINLINE void enc_emit_block(BitSink *kp, const uint32_t *m, uint32_t t0
     *kp = k;
 }
 
+#define ZWZ_DE_STORED_MIN 256u // literal tokens in a row before a stored region is considered
+
+// Token ranges (multiples of 32 tokens) that consist of literals only, are at least ZWZ_DE_STORED_MIN long and whose byte
+// histogram leaves a Huffman code less than n/256 bytes + 8 to gain: S.region[]. Returns their number (at most 8).
+ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t ntok) {
+    EncWarpSmem &S = enc_smem();
+    const unsigned lane = lane_id();
+    uint32_t nreg = 0;
+    uint32_t run_start = 0xffffffffu;
+    for (uint32_t base = 0; base < ntok + 32u && nreg < 8u; base += 32u) { // one extra step closes a run that reaches the end
+        const uint32_t i = base + lane;
+        const bool lit = i < ntok && tok_len(m[i]) == 0u;
+        const unsigned all = __ballot_sync(ZWZ_FULL, lit || i >= ntok);
+        const bool full = base < ntok && all == ZWZ_FULL;
+        if (full) {
+            if (run_start == 0xffffffffu) run_start = base;
+            continue;
+        }
+        if (run_start != 0xffffffffu) {
+            const uint32_t r0 = run_start, r1 = base < ntok ? base : ntok;
+            run_start = 0xffffffffu;
+            if (r1 - r0 >= ZWZ_DE_STORED_MIN) {
+                enc_hist_tokens(m, r0, r1, true); // into S.code: S.freq keeps the whole-chunk histogram
+                uint32_t nu;
+                const float h_bits = enc_entropy_bits(1u, &nu);
+                const float nb = (float) (r1 - r0);
+                if (8.f * nb - h_bits < nb * (1.f / 32.f) + 64.f) {
+                    if (lane == 0) {
+                        S.region[2u * nreg] = r0;
+                        S.region[2u * nreg + 1u] = r1;
+                    }
+                    ++nreg;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return nreg;
+}
+
+// The literal tokens [t0, t1) as one stored block (RFC 1951 §3.2.4): 3 header bits, pad to a byte boundary, LEN, NLEN, bytes.
+ZWZ_DEV_NOINLINE void enc_emit_stored_block(BitSink *kp, const uint32_t *m, uint32_t t0, uint32_t t1, bool last) {
+    EncWarpSmem &S = enc_smem();
+    BitSink k = *kp;
+    const unsigned lane = lane_id();
+    const uint32_t nbytes = t1 - t0; // <= 65 535: a chunk has no more bytes
+    const uint32_t at = k.nwords * 32u + k.fill + 3u;
+    const uint32_t pad = (8u - (at & 7u)) & 7u;
+    uint64_t v = 0;
+    uint32_t nb = 0;
+    if (lane == 0) {
+        v = last ? 1ull : 0ull; // BFINAL, BTYPE = 00, zero padding
+        nb = 3u + pad;
+    } else if (lane == 1u) {
+        v = (uint64_t) nbytes | ((uint64_t) (~nbytes & 0xffffu) << 16);
+        nb = 32u;
+    }
+    sink_put(S, k, v, nb);
+    for (uint32_t base = t0; base < t1; base += 128u) {
+        const uint32_t i = base + 4u * lane;
+        uint32_t w = 0, cnt = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j)
+            if (i + j < t1) {
+                w |= tok_byte(m[i + j]) << (8u * j);
+                ++cnt;
+            }
+        sink_put(S, k, (uint64_t) w, 8u * cnt);
+    }
+    *kp = k;
+}
+
+// The tokens [t0, t1) as one or more Huffman blocks. whole: S.freq already holds their histogram and extra_bits their extra
+// bits (the range is the whole chunk, straight from the parse).
+ZWZ_DEV_NOINLINE void enc_emit_range(BitSink *kp, const uint32_t *m, uint32_t t0r, uint32_t t1r, uint64_t extra_bits, bool last, bool whole) {
+    EncWarpSmem &S = enc_smem();
+    const unsigned lane = lane_id();
+    const uint32_t nt = t1r - t0r;
+    // base blocks of equal size, about ZWZ_DE_BASE tokens each (a short tail block would pay a whole header for nothing)
+    const uint32_t nbase = (nt + ZWZ_DE_BASE / 2u) / ZWZ_DE_BASE;
+    if (nbase <= 1u) {
+        if (!whole) extra_bits = enc_hist_tokens(m, t0r, t1r, false);
+        enc_emit_block(kp, m, t0r, t1r, extra_bits, last);
+        return;
+    }
+    const uint32_t bsz = (nt + nbase - 1u) / nbase;
+    uint32_t t0 = t0r, t1 = t0r + bsz;
+    uint64_t xb = enc_hist_tokens(m, t0, t1, false);
+    while (t1 < t1r) {
+        const uint32_t t2 = t1 + bsz < t1r ? t1 + bsz : t1r;
+        uint32_t *nf = S.code; // free until the next Huffman build
+        const uint64_t xn = enc_hist_tokens(m, t1, t2, true);
+        uint32_t ua, ub, uab;
+        const float ha = enc_entropy_bits(0u, &ua);
+        const float hb = enc_entropy_bits(1u, &ub);
+        const float hab = enc_entropy_bits(2u, &uab);
+        const float sep = ha + hb + 200.f + 4.f * (float) (ua + ub);
+        const float mer = hab + 100.f + 4.f * (float) uab;
+        if (mer <= sep) {
+            for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] += nf[i];
+            __syncwarp();
+            xb += xn;
+            t1 = t2;
+        } else {
+            enc_emit_block(kp, m, t0, t1, xb, false);
+            t0 = t1;
+            t1 = t2;
+            xb = enc_hist_tokens(m, t0, t1, false);
+        }
+    }
+    enc_emit_block(kp, m, t0, t1, xb, last);
+}
+
 ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     const unsigned lane = lane_id();
     const uint32_t n = job.raw_len[c];
@@ -587,6 +701,7 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
 
     // ---------------- parse ----------------
     uint32_t ntok = 0;
+    uint32_t lit_run = 0, max_lit_run = 0; // tokens since the last match / longest such stretch (stored-region candidates)
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)
     uint32_t m0 = lane < n ? m[lane] : 0u;
     for (uint32_t p = 0; p < n;) {
@@ -633,6 +748,12 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
             m[ntok + (uint32_t) __popc(tm & ((1u << lane) - 1u))] = tok;
         }
         ntok += (uint32_t) __popc(tm);
+        if (__ballot_sync(ZWZ_FULL, marked && take)) {
+            max_lit_run = lit_run > max_lit_run ? lit_run : max_lit_run;
+            lit_run = 0;
+        } else {
+            lit_run += (uint32_t) __popc(tm);
+        }
         p += J0;
         if (J0 == 32u) m0 = mnx;
         else m0 = p + lane < n ? m[p + lane] : 0u;
@@ -687,45 +808,31 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     }
 
     // ---------------- blocks ----------------
-    // Base blocks of ZWZ_DE_BASE tokens are merged left to right while one Huffman code over the union is estimated (empirical
-    // entropy + a header estimate) to cost no more than two separate ones; a merged run becomes one DEFLATE block. zlib cuts
-    // every 16 383 symbols regardless of content; adapting the cut is worth several percent on data whose statistics drift
-    // (bitmap-like), nothing on homogeneous text.
+    // Stored regions first: a stretch of >= 256 literal tokens whose bytes are (nearly) uniformly distributed — the body of a
+    // JPEG-like file behind its structured header — goes out as a STORED block between the Huffman blocks of its neighbours.
+    // zlib would code it with 8-bit literals (nothing gained), pay for it in every decoder (one Huffman symbol per byte instead
+    // of a copy), and let it flatten the neighbours' code lengths. Then, per remaining token range: base blocks of
+    // ZWZ_DE_BASE tokens are merged left to right while one Huffman code over the union is estimated (empirical entropy + a
+    // header estimate) to cost no more than two separate ones; a merged run becomes one DEFLATE block. zlib cuts every 16 383
+    // symbols regardless of content; adapting the cut is worth several percent on data whose statistics drift (bitmap-like),
+    // nothing on homogeneous text.
     const uint32_t cap_words = ((n + ZWZ_DEFLATE_MARGIN + 15u) & ~15u) >> 2; // zwz_deflate_bound(n) / 4
     BitSink k;
     sink_init(S, k, (uint32_t *) out, cap_words);
     sink_put(S, k, lane == 0 ? 0x9c78ull : 0ull, lane == 0 ? 16u : 0u); // RFC 1950 header 78 9C
-    // base blocks of equal size, about ZWZ_DE_BASE tokens each (a short tail block would pay a whole header for nothing)
-    const uint32_t nbase = (ntok + ZWZ_DE_BASE / 2u) / ZWZ_DE_BASE;
-    if (nbase <= 1u) {
-        enc_emit_block(&k, m, 0, ntok, extra_bits, true); // S.freq still holds the whole-chunk histogram from the parse
+    max_lit_run = lit_run > max_lit_run ? lit_run : max_lit_run;
+    const uint32_t nreg = max_lit_run >= ZWZ_DE_STORED_MIN ? enc_find_stored_regions(m, ntok) : 0u;
+    if (nreg == 0u) {
+        enc_emit_range(&k, m, 0, ntok, extra_bits, true, true); // S.freq still holds the whole-chunk histogram from the parse
     } else {
-        const uint32_t bsz = (ntok + nbase - 1u) / nbase;
-        uint32_t t0 = 0, t1 = bsz;
-        uint64_t xb = enc_hist_tokens(m, t0, t1, false);
-        while (t1 < ntok) {
-            const uint32_t t2 = t1 + bsz < ntok ? t1 + bsz : ntok;
-            uint32_t *nf = S.code; // free until the next Huffman build
-            const uint64_t xn = enc_hist_tokens(m, t1, t2, true);
-            uint32_t ua, ub, uab;
-            const float ha = enc_entropy_bits(0u, &ua);
-            const float hb = enc_entropy_bits(1u, &ub);
-            const float hab = enc_entropy_bits(2u, &uab);
-            const float sep = ha + hb + 200.f + 4.f * (float) (ua + ub);
-            const float mer = hab + 100.f + 4.f * (float) uab;
-            if (mer <= sep) {
-                for (uint32_t i = lane; i < 320u; i += 32u) S.freq[i] += nf[i];
-                __syncwarp();
-                xb += xn;
-                t1 = t2;
-            } else {
-                enc_emit_block(&k, m, t0, t1, xb, false);
-                t0 = t1;
-                t1 = t2;
-                xb = enc_hist_tokens(m, t0, t1, false);
-            }
+        uint32_t t = 0;
+        for (uint32_t r = 0; r < nreg; ++r) {
+            const uint32_t r0 = S.region[2u * r], r1 = S.region[2u * r + 1u];
+            if (r0 > t) enc_emit_range(&k, m, t, r0, 0, false, false);
+            enc_emit_stored_block(&k, m, r0, r1, r1 == ntok);
+            t = r1;
         }
-        enc_emit_block(&k, m, t0, t1, xb, true);
+        if (t < ntok) enc_emit_range(&k, m, t, ntok, 0, true, false);
     }
     // pad to a byte boundary, Adler-32 big-endian
     const uint32_t adler = job.adler[c];

@@ -2,12 +2,19 @@
 //
 // The reference runs a producer thread that cuts files into 65 535-byte chunks, a mutex queue, ONE consumer thread that
 // calls zlib per chunk, and a writer that re-reads each source file for its MD5. Here the rank's files are planned into
-// batches of whole files up front; W workers (pipeline.hpp) each take a batch, read its files into their page-locked staging
-// buffer, make ONE trip through the GPU (zwz_compress_files: upload once, deflate every chunk, MD5 every file from the same
-// resident bytes, pack, download), serialise the records in the reference's byte layout (compression.cpp:73-104) and write
-// them at the batch's offset of the archive. Offsets are handed out in batch order, so the archive is the same bytes for
-// any W: record order is file order then sequence order, which is exactly what the reference produces with
-// NUM_CONSUMERS = 1.
+// batches up front — whole files per batch, and files larger than a batch cut into chunk-aligned SEGMENTS that are batches
+// of their own — and W workers (pipeline.hpp) each take a batch: read it into their page-locked staging buffer (several
+// reader threads per batch: 370 000 small files are open/read/close bound), make ONE trip through the GPU, serialise the
+// records in the reference's byte layout (compression.cpp:73-104) and take the batch's place in the archive. Offsets are
+// handed out in batch order, so the archive is the same bytes for any W: record order is file order then sequence order,
+// which is exactly what the reference produces with NUM_CONSUMERS = 1.
+//
+// MD5 is off the batch critical path. A file's digest is one serial chain (~0.13 GB/s per file), so:
+//   * batches of whole files go through zwz_compress_files_async: the call returns when the packed streams are back, the
+//     digests follow on the context's second stream; the serialised records wait in memory (two batches per worker) until
+//     zwz_wait delivers the digests, then go to the archive with ONE pwrite at the offset reserved earlier;
+//   * a file cut into segments is hashed by a separate hasher thread that streams it through zwz_md5_update_device on its
+//     own context while all workers deflate its segments; only the record that carries the digest waits for it.
 #include "pipeline.hpp"
 
 #include <algorithm>
@@ -16,6 +23,7 @@
 #include <cstring>
 #include <fcntl.h>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <sstream>
 #include <unistd.h>
@@ -29,20 +37,30 @@ namespace {
 struct PlannedFile {
     std::string relpath;
     uint64_t size = 0; // from stat at planning time; the bytes actually read decide the records
+    int big = -1;      // index into Job::bigs when the file is cut into segments
 };
 struct Batch {
-    size_t first = 0, count = 0;
+    size_t first = 0, count = 0; // files [first, first + count); a segment: count == 1
     uint64_t bytes = 0;
-    bool big = false; // one file larger than the staging buffer: streamed through in segments
+    bool segment = false;
+    uint64_t seg_off = 0, seg_len = 0; // byte range of the file; a whole number of chunks unless it is the last segment
+    bool seg_last = false;
 };
 struct LoadedFile {
     const std::string *relpath;
     uint64_t off = 0, size = 0; // inside the staging buffer
 };
+// a file that is cut into segments: its sequence ids continue across batches (the split rule may add records), and its
+// digest comes from the hasher thread
+struct BigFile {
+    size_t file = 0;
+    int next_seq = 0;                    // guarded by the commit order
+    std::shared_future<std::string> md5; // 32 hex characters ("" when the file could not be read)
+};
 
 // compression.cpp:73-104: i32 total_size, i32 path_len, path, i32 sequence_id, u8 is_last_chunk, payload[, 32 hex chars]
 void append_record(std::vector<char> &out, const std::string &relpath, int sequence_id, bool is_last_chunk, const uint8_t *payload,
-                   uint32_t payload_len, const char *md5_hex, RunStats &st) {
+                   uint32_t payload_len, RunStats &st) {
     int path_length = static_cast<int>(relpath.size());
     int total_size = (int) sizeof(path_length) + path_length + (int) sizeof(sequence_id) + (int) sizeof(bool) + (int) payload_len;
     size_t o = out.size();
@@ -55,19 +73,19 @@ void append_record(std::vector<char> &out, const std::string &relpath, int seque
     std::memcpy(p, &sequence_id, 4);
     p[4] = is_last_chunk ? 1 : 0;
     std::memcpy(p + 5, payload, payload_len);
-    if (is_last_chunk) std::memcpy(p + 5 + payload_len, md5_hex, MD5_DATA_SIZE);
+    if (is_last_chunk) std::memset(p + 5 + payload_len, '0', MD5_DATA_SIZE); // filled in when the digest arrives
     st.records++;
     st.payload_bytes += payload_len;
 }
 
 // one chunk -> one record, or two when the split rule fired (the reference would have silently truncated this chunk)
 void emit_chunk(std::vector<char> &out, const std::string &relpath, int &seq, bool last_chunk_of_file, const uint8_t *payload,
-                const zwz_deflate_result &r, const char *md5_hex, RunStats &st) {
+                const zwz_deflate_result &r, RunStats &st) {
     if (r.len1 == 0) {
-        append_record(out, relpath, seq++, last_chunk_of_file, payload, r.len0, md5_hex, st);
+        append_record(out, relpath, seq++, last_chunk_of_file, payload, r.len0, st);
     } else {
-        append_record(out, relpath, seq++, false, payload, r.len0, md5_hex, st);
-        append_record(out, relpath, seq++, last_chunk_of_file, payload + r.len0, r.len1, md5_hex, st);
+        append_record(out, relpath, seq++, false, payload, r.len0, st);
+        append_record(out, relpath, seq++, last_chunk_of_file, payload + r.len0, r.len1, st);
     }
 }
 
@@ -111,6 +129,7 @@ struct Job {
     const std::string &input_dir;
     const std::vector<PlannedFile> &files;
     const std::vector<Batch> &batches;
+    std::vector<BigFile> &bigs;
     int fd;
     size_t cap;     // staging capacity of a worker
     size_t out_cap; // enough for the packed streams of any planned batch: page-locked buffers are sized once per worker
@@ -119,13 +138,20 @@ struct Job {
     std::atomic<size_t> next_batch{0};
     OrderedCommit order;
     uint64_t archive_off = 0; // guarded by the commit order
-    Job(const std::string &in, const std::vector<PlannedFile> &f, const std::vector<Batch> &b, int fd_, size_t cap_, int level_, int device_)
-        : input_dir(in), files(f), batches(b), fd(fd_), cap(cap_), out_cap(0), level(level_), device(device_) {
+    Job(const std::string &in, const std::vector<PlannedFile> &f, const std::vector<Batch> &b, std::vector<BigFile> &bg, int fd_, size_t cap_,
+        int level_, int device_)
+        : input_dir(in), files(f), batches(b), bigs(bg), fd(fd_), cap(cap_), out_cap(0), level(level_), device(device_) {
         size_t max_files = 1;
         for (const auto &x : b) max_files = std::max(max_files, x.count);
         out_cap = cap + (cap / CHUNK_SIZE + max_files + 16) * 64 + 4096;
     }
 };
+
+// the digest of a file that is cut into segments: the whole file streamed through the GPU's MD5 update/final pair on the
+// hasher's own context (verification.cpp:13-22 is the same loop with 1 024-byte pieces on the CPU)
+std::string hash_big_file(int device, int hasher, const std::string &full) {
+    return md5_of_file_ctx(worker_ctx(device, 64 + hasher), full);
+}
 
 class Worker {
   public:
@@ -133,40 +159,114 @@ class Worker {
 
     void run() {
         for (;;) {
+            Pending &p = pend_[turn_++ & 1];
+            finalize(p); // its buffers are about to be reused. BEFORE a batch index is taken: waiting for digests while holding
+                         // an index would keep every later batch from committing
             size_t b = job_.next_batch.fetch_add(1);
-            if (b >= job_.batches.size()) return;
+            if (b >= job_.batches.size()) break;
             const Batch &batch = job_.batches[b];
-            if (batch.big)
-                big_file(b, job_.files[batch.first]);
+            if (batch.segment)
+                segment(b, batch, p);
             else
-                small_files(b, batch);
+                small_files(b, batch, p);
         }
+        finalize(pend_[turn_ & 1]);
+        finalize(pend_[(turn_ + 1) & 1]);
     }
 
   private:
-    void small_files(size_t b, const Batch &batch) {
+    // a batch whose records are serialised and whose place in the archive is reserved, waiting for its digests
+    struct Pending {
+        bool active = false;
+        uint64_t ticket = 0;
+        std::vector<char> records;
+        uint64_t archive_off = 0;
+        std::vector<size_t> md5_pos;   // per file of the batch: where its 32 hex characters go inside `records`
+        std::vector<uint8_t> digest;   // 16 bytes per file, filled by zwz_wait
+        std::shared_future<std::string> big_md5; // a segment that carries its file's digest
+        bool has_big_md5 = false;
         RunStats st;
+    };
+
+    void finalize(Pending &p) {
+        if (!p.active) return;
+        p.active = false;
+        double t0 = now_seconds();
+        if (p.ticket && zwz_wait(ctx_, p.ticket) != ZWZ_OK) throw std::runtime_error(std::string("zwz_wait: ") + zwz_last_error(ctx_));
+        for (size_t i = 0; i < p.md5_pos.size(); ++i) {
+            if (p.has_big_md5) {
+                const std::string hex = p.big_md5.get();
+                // verification.cpp:8-11: an unreadable file gives "" and NOTHING is written — here the field stays zeros,
+                // which keeps the archive parseable
+                if (hex.size() == MD5_DATA_SIZE) std::memcpy(p.records.data() + p.md5_pos[i], hex.data(), MD5_DATA_SIZE);
+            } else {
+                zwz_md5_hex(&p.digest[i * 16], p.records.data() + p.md5_pos[i]);
+            }
+        }
+        p.st.t_gpu += now_seconds() - t0;
+        t0 = now_seconds();
+        write_at(job_.fd, p.records.data(), p.records.size(), p.archive_off);
+        p.st.t_write += now_seconds() - t0;
+        merge_stats(p.st);
+        p.st = RunStats();
+    }
+
+    // takes this batch's place in the archive, in batch order; the write itself runs unordered, later
+    template <class F> void commit(size_t b, Pending &p, const std::string &log_text, F &&ordered_fixup) {
+        job_.order.wait_turn(b);
+        ordered_fixup();
+        p.archive_off = job_.archive_off;
+        job_.archive_off += p.records.size();
+        if (!log_text.empty()) std::cerr << log_text << std::flush;
+        job_.order.done(b);
+        p.active = true;
+    }
+
+    void small_files(size_t b, const Batch &batch, Pending &p) {
+        RunStats &st = p.st;
         std::ostringstream log;
         stage_.reserve(job_.cap + 64);
-        // ---- read
+        // ---- read: the files' places in the staging buffer are known from the plan, so readers work independently
         double t0 = now_seconds();
+        const size_t nfiles = batch.count;
+        std::vector<uint64_t> at(nfiles + 1, 0), got(nfiles, 0);
+        std::vector<char> opened(nfiles, 0);
+        for (size_t i = 0; i < nfiles; ++i) at[i + 1] = at[i] + job_.files[batch.first + i].size;
+        parallel_for(nfiles, io_threads(), [&](size_t i) {
+            const PlannedFile &pf = job_.files[batch.first + i];
+            std::string full = job_.input_dir + "/" + pf.relpath;
+            int fd = ::open(full.c_str(), O_RDONLY);
+            if (fd < 0) return;
+            opened[i] = 1;
+            uint64_t done = 0;
+            while (done < pf.size) {
+                ssize_t r = ::read(fd, stage_.data() + at[i] + done, pf.size - done);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) break;
+                done += (uint64_t) r;
+            }
+            ::close(fd);
+            got[i] = done;
+        });
+        // compact (a file that shrank or vanished since the plan leaves a hole)
         std::vector<LoadedFile> loaded;
+        loaded.reserve(nfiles);
         uint64_t used = 0;
-        for (size_t i = batch.first; i < batch.first + batch.count; ++i) {
-            const PlannedFile &pf = job_.files[i];
-            std::string full = (fs::path(job_.input_dir) / pf.relpath).string();
-            std::FILE *f = std::fopen(full.c_str(), "rb");
-            if (!f) { // compression.cpp:45-48: report and skip
-                log << "Error opening source file: " << full << "\n";
+        for (size_t i = 0; i < nfiles; ++i) {
+            const PlannedFile &pf = job_.files[batch.first + i];
+            if (!opened[i]) { // compression.cpp:45-48: report and skip
+                log << "Error opening source file: " << job_.input_dir << "/" << pf.relpath << "\n";
                 continue;
             }
-            size_t got = pf.size ? std::fread(stage_.data() + used, 1, pf.size, f) : 0;
-            std::fclose(f);
-            loaded.push_back({&pf.relpath, used, got});
-            used += got;
+            if (used != at[i] && got[i]) std::memmove(stage_.data() + used, stage_.data() + at[i], got[i]);
+            loaded.push_back({&pf.relpath, used, got[i]});
+            used += got[i];
         }
-        st.t_read = now_seconds() - t0;
-        records_.clear();
+        st.t_read += now_seconds() - t0;
+        p.records.clear();
+        p.md5_pos.clear();
+        p.ticket = 0;
+        p.has_big_md5 = false;
         if (!loaded.empty()) {
             // ---- GPU
             const uint32_t nf = (uint32_t) loaded.size();
@@ -176,130 +276,120 @@ class Worker {
             const uint64_t nc = zwz_count_chunks(foff.data(), nf);
             std::vector<uint64_t> poff(nc + 1);
             std::vector<zwz_deflate_result> res(nc);
-            std::vector<uint8_t> digest((size_t) nf * 16);
+            p.digest.assign((size_t) nf * 16, 0);
             out_.reserve(std::max<size_t>(job_.out_cap, used + nc * 64 + 4096));
             t0 = now_seconds();
-            int rc = zwz_compress_files(ctx_, stage_.data(), foff.data(), nf, job_.level, out_.data(), out_.cap, poff.data(), res.data(),
-                                        digest.data());
+            int rc = zwz_compress_files_async(ctx_, stage_.data(), foff.data(), nf, job_.level, out_.data(), out_.cap, poff.data(), res.data(),
+                                              p.digest.data(), &p.ticket);
             if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_compress_files: ") + zwz_last_error(ctx_));
-            st.t_gpu = now_seconds() - t0;
+            st.t_gpu += now_seconds() - t0;
             // ---- serialise
             t0 = now_seconds();
+            p.records.reserve((size_t) poff[nc] + nc * 24 + (size_t) nf * 96);
             size_t c = 0;
             for (uint32_t i = 0; i < nf; ++i) {
-                char hex[32];
-                zwz_md5_hex(&digest[(size_t) i * 16], hex);
                 uint64_t nch = loaded[i].size / CHUNK_SIZE + 1;
                 int seq = 0;
-                for (uint64_t k = 0; k < nch; ++k, ++c)
-                    emit_chunk(records_, *loaded[i].relpath, seq, k + 1 == nch, out_.data() + poff[c], res[c], hex, st);
+                for (uint64_t k = 0; k < nch; ++k, ++c) emit_chunk(p.records, *loaded[i].relpath, seq, k + 1 == nch, out_.data() + poff[c], res[c], st);
+                p.md5_pos.push_back(p.records.size() - MD5_DATA_SIZE);
                 st.files++;
                 st.raw_bytes += loaded[i].size;
                 if (config().verbose) log << "md5 value size: " << MD5_DATA_SIZE << "\n"; // compression.cpp:100
             }
-            st.t_write = now_seconds() - t0;
+            st.t_write += now_seconds() - t0;
         }
-        // ---- commit: take this batch's place in the archive, in batch order; the write itself runs unordered
-        job_.order.wait_turn(b);
-        uint64_t at = job_.archive_off;
-        job_.archive_off += records_.size();
-        std::string text = log.str();
-        if (!text.empty()) std::cerr << text << std::flush;
-        job_.order.done(b);
-        t0 = now_seconds();
-        write_at(job_.fd, records_.data(), records_.size(), at);
-        st.t_write += now_seconds() - t0;
-        merge_stats(st);
+        commit(b, p, log.str(), [] {});
     }
 
-    // A file larger than the staging buffer: segments of k x 65 535 bytes with k a multiple of 64, so every segment but
-    // the last is also a whole number of 64-byte MD5 blocks and the digest can be chained through zwz_md5_update_device.
-    // The worker keeps its turn for the whole file (its records must stay contiguous and their total size is only known
-    // at the end).
-    void big_file(size_t b, const PlannedFile &pf) {
-        RunStats st;
-        std::string full = (fs::path(job_.input_dir) / pf.relpath).string();
-        job_.order.wait_turn(b);
-        std::FILE *f = std::fopen(full.c_str(), "rb");
-        if (!f) {
-            std::cerr << "Error opening source file: " << full << std::endl;
-            job_.order.done(b);
-            return;
-        }
-        void *dev = nullptr;
-        try {
-            stage_.reserve(job_.cap + 64);
-            const uint64_t seg_chunks = std::max<uint64_t>(64, (job_.cap / CHUNK_SIZE) / 64 * 64);
-            const uint64_t seg_bytes = seg_chunks * CHUNK_SIZE;
-            if (zwz_malloc_device(ctx_, seg_bytes + 64, &dev) != ZWZ_OK) throw std::runtime_error("zwz: device allocation failed");
-            std::vector<uint8_t> host_seg; // staging may be smaller than a segment when batch_bytes is tiny
-            uint8_t *buf = stage_.data();
-            if (seg_bytes > job_.cap) {
-                host_seg.resize(seg_bytes);
-                buf = host_seg.data();
-            }
-            uint32_t state[4];
-            zwz_md5_state_init(state, 1);
-            uint64_t total = 0;
-            int seq = 0;
-            for (;;) {
-                size_t got = std::fread(buf, 1, seg_bytes, f);
-                total += got;
-                bool final_seg = got < seg_bytes;
-                uint64_t zero = 0;
-                if (got && zwz_memcpy_h2d(ctx_, dev, buf, got) != ZWZ_OK) throw std::runtime_error("zwz: h2d failed");
-                char hex[32];
-                if (!final_seg) {
-                    uint64_t len = got;
-                    if (zwz_md5_update_device(ctx_, state, (const uint8_t *) dev, &zero, &len, 1, nullptr) != ZWZ_OK)
-                        throw std::runtime_error(std::string("zwz: md5 update: ") + zwz_last_error(ctx_));
-                } else {
-                    uint64_t fullb = got & ~(uint64_t) 63, tail = got - fullb;
-                    uint8_t digest[16];
-                    if (fullb && zwz_md5_update_device(ctx_, state, (const uint8_t *) dev, &zero, &fullb, 1, nullptr) != ZWZ_OK)
-                        throw std::runtime_error(std::string("zwz: md5 update: ") + zwz_last_error(ctx_));
-                    if (zwz_md5_final_device(ctx_, state, (const uint8_t *) dev, &fullb, &tail, &total, 1, digest, nullptr) != ZWZ_OK)
-                        throw std::runtime_error(std::string("zwz: md5 final: ") + zwz_last_error(ctx_));
-                    zwz_md5_hex(digest, hex);
+    // One segment of a file that does not fit a batch: k x 65 535 bytes (the last one: the rest, with the possibly empty tail
+    // chunk). Deflate only — the file's digest comes from the hasher thread.
+    void segment(size_t b, const Batch &batch, Pending &p) {
+        RunStats &st = p.st;
+        const PlannedFile &pf = job_.files[batch.first];
+        BigFile &big = job_.bigs[(size_t) pf.big];
+        const std::string full = job_.input_dir + "/" + pf.relpath;
+        stage_.reserve(job_.cap + 64);
+        p.records.clear();
+        p.md5_pos.clear();
+        p.ticket = 0;
+        p.has_big_md5 = false;
+        std::string log;
+        double t0 = now_seconds();
+        int fd = ::open(full.c_str(), O_RDONLY);
+        std::atomic<uint64_t> got{0};
+        if (fd >= 0) {
+            const uint64_t piece = (uint64_t) 8 << 20;
+            const size_t npieces = (size_t) ((batch.seg_len + piece - 1) / piece);
+            parallel_for(npieces, io_threads(), [&](size_t i) {
+                uint64_t o = i * piece, n = std::min<uint64_t>(piece, batch.seg_len - o), done = 0;
+                while (done < n) {
+                    ssize_t r = ::pread(fd, stage_.data() + o + done, n - done, (off_t) (batch.seg_off + o + done));
+                    if (r < 0 && errno == EINTR) continue;
+                    if (r <= 0) break;
+                    done += (uint64_t) r;
                 }
-                // chunks of this segment; only the final segment carries the (possibly empty) tail chunk
-                uint64_t nfull = got / CHUNK_SIZE;
-                uint64_t nch = final_seg ? nfull + 1 : nfull;
-                std::vector<uint64_t> off(nch), poff(nch + 1);
-                std::vector<uint32_t> len(nch);
-                std::vector<zwz_deflate_result> res(nch);
-                for (uint64_t k = 0; k < nch; ++k) {
-                    off[k] = k * CHUNK_SIZE;
-                    len[k] = (uint32_t) std::min<uint64_t>(CHUNK_SIZE, got - k * CHUNK_SIZE);
-                }
-                out_.reserve(got + nch * 64 + 4096);
-                if (nch && zwz_deflate_batch(ctx_, buf, off.data(), len.data(), (uint32_t) nch, out_.data(), out_.cap, poff.data(), res.data(),
-                                             job_.level) != ZWZ_OK)
-                    throw std::runtime_error(std::string("zwz_deflate_batch: ") + zwz_last_error(ctx_));
-                records_.clear();
-                for (uint64_t k = 0; k < nch; ++k)
-                    emit_chunk(records_, pf.relpath, seq, final_seg && k + 1 == nch, out_.data() + poff[k], res[k], hex, st);
-                write_at(job_.fd, records_.data(), records_.size(), job_.archive_off);
-                job_.archive_off += records_.size();
-                if (final_seg) break;
-            }
-            st.files++;
-            st.raw_bytes += total;
-        } catch (...) {
-            std::fclose(f);
-            if (dev) zwz_free_device(ctx_, dev);
-            throw;
+                got += done;
+            });
+            ::close(fd);
+        } else if (batch.seg_off == 0) {
+            log = "Error opening source file: " + full + "\n";
         }
-        std::fclose(f);
-        zwz_free_device(ctx_, dev);
-        job_.order.done(b);
-        merge_stats(st);
+        st.t_read += now_seconds() - t0;
+        const bool usable = fd >= 0 && got.load() == batch.seg_len; // a file that changed under us: its remaining records are dropped
+        int provisional = (int) (batch.seg_off / CHUNK_SIZE);
+        if (usable) {
+            const uint64_t nfull = batch.seg_len / CHUNK_SIZE;
+            const uint64_t nch = batch.seg_last ? nfull + 1 : nfull;
+            std::vector<uint64_t> off(nch), poff(nch + 1);
+            std::vector<uint32_t> len(nch);
+            std::vector<zwz_deflate_result> res(nch);
+            for (uint64_t k = 0; k < nch; ++k) {
+                off[k] = k * CHUNK_SIZE;
+                len[k] = (uint32_t) std::min<uint64_t>(CHUNK_SIZE, batch.seg_len - k * CHUNK_SIZE);
+            }
+            out_.reserve(std::max<size_t>(job_.out_cap, batch.seg_len + nch * 64 + 4096));
+            t0 = now_seconds();
+            if (nch && zwz_deflate_batch(ctx_, stage_.data(), off.data(), len.data(), (uint32_t) nch, out_.data(), out_.cap, poff.data(), res.data(),
+                                         job_.level) != ZWZ_OK)
+                throw std::runtime_error(std::string("zwz_deflate_batch: ") + zwz_last_error(ctx_));
+            st.t_gpu += now_seconds() - t0;
+            t0 = now_seconds();
+            p.records.reserve((size_t) poff[nch] + nch * (24 + pf.relpath.size()) + 64);
+            int seq = provisional;
+            for (uint64_t k = 0; k < nch; ++k) emit_chunk(p.records, pf.relpath, seq, batch.seg_last && k + 1 == nch, out_.data() + poff[k], res[k], st);
+            if (batch.seg_last) {
+                p.md5_pos.push_back(p.records.size() - MD5_DATA_SIZE);
+                p.big_md5 = big.md5;
+                p.has_big_md5 = true;
+                st.files++;
+            }
+            st.raw_bytes += batch.seg_len;
+            st.t_write += now_seconds() - t0;
+        }
+        commit(b, p, log, [&] {
+            // sequence ids continue where the previous segment stopped (they run ahead of the chunk index when the split rule
+            // fired earlier in the file): renumber in place, the id sits at a fixed place of every record header
+            const int base = big.next_seq;
+            int count = 0;
+            size_t o = 0;
+            while (o + 8 <= p.records.size()) {
+                int total_size, path_length;
+                std::memcpy(&total_size, p.records.data() + o, 4);
+                std::memcpy(&path_length, p.records.data() + o + 4, 4);
+                int seq = base + count++;
+                std::memcpy(p.records.data() + o + 8 + path_length, &seq, 4);
+                const bool last = p.records[o + 12 + (size_t) path_length] != 0;
+                o += 4 + (size_t) total_size + (last ? MD5_DATA_SIZE : 0);
+            }
+            big.next_seq = base + count;
+        });
     }
 
     Job &job_;
     zwz_ctx *ctx_;
     PinnedBuf stage_, out_;
-    std::vector<char> records_;
+    Pending pend_[2];
+    unsigned turn_ = 0;
 };
 
 } // namespace
@@ -330,28 +420,54 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
             warm_error = std::current_exception();
         }
     });
-    // the deal, then the plan: whole files per batch, in deal order
+    // the deal, then the plan, in deal order
     std::vector<PlannedFile> files;
     int file_number = 0, next_file_number = world_rank;
     std::string file_path;
     while (std::getline(record_file, file_path)) {
         if (file_number == next_file_number) {
             next_file_number += cfg.world_size;
-            std::error_code ec;
-            uint64_t size = fs::file_size(fs::path(input_dir) / file_path, ec);
-            files.push_back({file_path, ec ? 0 : size});
+            files.push_back({file_path, 0, -1});
         }
         file_number++;
     }
-    const size_t cap = cfg.batch_bytes;
+    parallel_for(files.size(), io_threads() * 2, [&](size_t i) {
+        std::error_code ec;
+        uint64_t size = fs::file_size(fs::path(input_dir) / files[i].relpath, ec);
+        files[i].size = ec ? 0 : size;
+    });
+    uint64_t total_bytes = 0;
+    for (const auto &f : files) total_bytes += f.size;
+    // batches small enough that every worker gets several (a 200 MB job in one 128 MB batch would leave the pool idle)
+    const int pool = worker_count();
+    const size_t cap = (size_t) std::min<uint64_t>(cfg.batch_bytes, std::max<uint64_t>((uint64_t) 8 << 20, total_bytes / ((uint64_t) pool * 3) + 1));
+    const uint64_t seg_bytes = std::max<uint64_t>(1, cap / CHUNK_SIZE) * CHUNK_SIZE; // whole chunks
     std::vector<Batch> batches;
+    std::vector<BigFile> bigs;
     for (size_t i = 0; i < files.size(); ++i) {
         if (files[i].size + 64 > cap) {
-            batches.push_back({i, 1, files[i].size, true});
+            files[i].big = (int) bigs.size();
+            bigs.push_back({i, 0, {}});
+            for (uint64_t o = 0;; o += seg_bytes) {
+                const bool last = files[i].size - o < seg_bytes; // the last segment carries the tail chunk (possibly empty)
+                Batch s;
+                s.first = i;
+                s.count = 1;
+                s.segment = true;
+                s.seg_off = o;
+                s.seg_len = last ? files[i].size - o : seg_bytes;
+                s.bytes = s.seg_len;
+                s.seg_last = last;
+                batches.push_back(s);
+                if (last) break;
+            }
             continue;
         }
-        if (batches.empty() || batches.back().big || batches.back().bytes + files[i].size > cap || batches.back().count >= 262144)
-            batches.push_back({i, 0, 0, false});
+        if (batches.empty() || batches.back().segment || batches.back().bytes + files[i].size > cap || batches.back().count >= 262144) {
+            Batch nb;
+            nb.first = i;
+            batches.push_back(nb);
+        }
         batches.back().count++;
         batches.back().bytes += files[i].size;
     }
@@ -361,18 +477,37 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         ::close(fd);
         std::rethrow_exception(warm_error);
     }
-    Job job(input_dir, files, batches, fd, cap, cfg.level, cfg.device);
-    const int workers = (int) std::min<size_t>((size_t) worker_count(), std::max<size_t>(1, batches.size()));
+    // hashers for the files that are cut into segments (at most 4 at a time; each streams its file once more through the GPU)
+    std::vector<std::thread> hashers;
+    std::vector<std::promise<std::string>> promises(bigs.size());
+    for (size_t k = 0; k < bigs.size(); ++k) bigs[k].md5 = promises[k].get_future().share();
+    std::atomic<size_t> next_big{0};
+    for (size_t h = 0; h < std::min<size_t>(bigs.size(), 4); ++h)
+        hashers.emplace_back([&, h] {
+            for (;;) {
+                size_t k = next_big.fetch_add(1);
+                if (k >= bigs.size()) return;
+                try {
+                    promises[k].set_value(hash_big_file(cfg.device, (int) h, input_dir + "/" + files[bigs[k].file].relpath));
+                } catch (...) {
+                    promises[k].set_exception(std::current_exception());
+                }
+            }
+        });
+    Job job(input_dir, files, batches, bigs, fd, std::max<size_t>(cap, (size_t) seg_bytes), cfg.level, cfg.device);
+    const int workers = (int) std::min<size_t>((size_t) pool, std::max<size_t>(1, batches.size()));
+    std::exception_ptr failure;
     try {
         run_workers(workers, job.order, [&](int w) {
             Worker worker(job, w);
             worker.run();
         });
     } catch (...) {
-        ::close(fd);
-        throw;
+        failure = std::current_exception();
     }
+    for (auto &t : hashers) t.join();
     ::close(fd);
+    if (failure) std::rethrow_exception(failure);
     std::cout << "Rank: " << world_rank << " - Total processed file: " << file_number << std::endl;
     print_timing("compress");
 }

@@ -8,6 +8,7 @@
 // rest of the GPU meanwhile), copies overlap kernels, and file I/O overlaps both. Results are committed in batch order, so
 // the archive bytes and the console output do not depend on W or on timing.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <exception>
@@ -23,7 +24,8 @@ namespace zwzhost {
 
 zwz_ctx *ctx_for(int device);
 zwz_ctx *worker_ctx(int device, int worker); // worker 0 shares ctx_for(device); the others get their own, created on first use
-int worker_count();                          // ZWZ_WORKERS, clamped to [1, 8]
+int worker_count();                          // ZWZ_WORKERS (default: host cores / ranks on this box / 2), clamped to [1, 12]
+int io_threads();                            // ZWZ_IO_THREADS: reader/writer threads a worker uses inside one batch (default 4)
 std::string md5_of_file_ctx(zwz_ctx *ctx, const std::string &file_path);
 
 // batch b may commit only after batches 0..b-1 have
@@ -79,6 +81,31 @@ inline void run_workers(int n, OrderedCommit &order, const std::function<void(in
         });
     for (auto &t : threads) t.join();
     if (first) std::rethrow_exception(first);
+}
+
+// fn(i) for i in [0, n) on up to `threads` threads (the caller's included); fn must not throw. Used for the file I/O inside
+// one batch: 370 000 small files are bound by open/read/close (resp. open/write/close) latency, not by bandwidth.
+template <class F> inline void parallel_for(size_t n, int threads, F &&fn) {
+    if (n == 0) return;
+    const size_t nt = std::min<size_t>((size_t) std::max(1, threads), n);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    const size_t grain = std::max<size_t>(1, n / (nt * 8));
+    auto body = [&] {
+        for (;;) {
+            size_t a = next.fetch_add(grain);
+            if (a >= n) return;
+            size_t b = std::min(n, a + grain);
+            for (size_t i = a; i < b; ++i) fn(i);
+        }
+    };
+    std::vector<std::thread> ts;
+    for (size_t t = 1; t < nt; ++t) ts.emplace_back(body);
+    body();
+    for (auto &t : ts) t.join();
 }
 
 // grow-only page-locked host buffer (copies from/to it run at full PCIe speed and asynchronously)

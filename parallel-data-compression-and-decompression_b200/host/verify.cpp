@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 
 namespace zwzhost {
 
@@ -53,8 +54,24 @@ zwz_ctx *worker_ctx(int device, int worker) {
 
 int worker_count() {
     const char *e = std::getenv("ZWZ_WORKERS");
-    int w = (e && *e) ? std::atoi(e) : 3;
-    return w < 1 ? 1 : (w > 8 ? 8 : w);
+    int w;
+    if (e && *e) {
+        w = std::atoi(e);
+    } else {
+        // every worker is a host thread that reads, serialises and writes besides driving its CUDA stream: half the cores this
+        // rank may use (the ranks of one box share them), at least 3
+        int cores = (int) std::thread::hardware_concurrency();
+        int local_ranks = std::max(1, std::min(config().world_size, std::max(1, visible_gpu_count())));
+        w = std::max(3, cores / local_ranks / 2);
+        w = std::min(w, 8);
+    }
+    return w < 1 ? 1 : (w > 12 ? 12 : w);
+}
+
+int io_threads() {
+    const char *e = std::getenv("ZWZ_IO_THREADS");
+    int t = (e && *e) ? std::atoi(e) : 4;
+    return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
 
 // Streams the file through the device in pieces (the reference streams 1 024-byte reads through MD5_Update,
