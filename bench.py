@@ -74,15 +74,11 @@ def build_shard(workload: str, files: int, rank: int, world: int) -> Shard:
         all_sizes = corpus.c2_sizes(files * world, seed)
         order = np.argsort(-all_sizes, kind="stable")
         mine = order[rank::world]
-        buf, offs, sizes = corpus.c2_buffer(len(mine), seed + 7919 * rank)
+        # every file is generated AT its dealt size, so a file is one JPEG-like or one bitmap-like file (round 1 cut a
+        # buffer of generated files at the dealt boundaries, which mixed the two classes inside most files)
         want = all_sizes[mine]
-        tot = int(want.sum())
-        if tot > len(buf):
-            extra, _, _ = corpus.c2_buffer(int((tot - len(buf)) // 6000 + 1000), seed + 7919 * rank + 1)
-            buf = np.concatenate([buf, extra])
-        buf = np.ascontiguousarray(buf[:tot])
-        foffs = np.zeros(len(want) + 1, dtype=np.int64)
-        np.cumsum(want, out=foffs[1:])
+        buf, foffs, _ = corpus.c2_buffer(len(mine), seed + 7919 * rank, sizes=want)
+        tot = int(foffs[-1])
         return Shard(buf, tot, foffs, f"C2: {files} image-like files/GPU (70% JPEG-like, 30% bitmap-like), one chunk each")
     if workload == "c3":
         size = files  # bytes

@@ -49,6 +49,9 @@ struct EncWarpSmem {
     uint32_t stage[64];     // bit sink staging window
     uint32_t misc[8];
     uint32_t region[16];    // stored regions of the chunk: token ranges [region[2i], region[2i+1])
+    uint32_t tflags[ZWZ_SCR_FLAG_WORDS]; // bit t: the 32-position tile t holds a match (its scratch words are valid)
+    uint16_t kb_tok[66];    // token index / byte position of the first parse step inside every 1 024-byte stretch
+    uint16_t kb_pos[66];
 };
 #define ZWZ_DE_SMEM (ZWZ_DE_WARPS * (uint32_t) sizeof(zwz::EncWarpSmem))
 
@@ -550,39 +553,38 @@ ZWZ_DEV_NOINLINE void enc_emit_block(BitSink *kp, const uint32_t *m, uint32_t t0
     *kp = k;
 }
 
-#define ZWZ_DE_STORED_MIN 256u // literal tokens in a row before a stored region is considered
+#define ZWZ_DE_STORED_MIN 512u // literal tokens in a row before a stored region is considered
 
-// Token ranges (multiples of 32 tokens) that consist of literals only, are at least ZWZ_DE_STORED_MIN long and whose byte
-// histogram leaves a Huffman code less than n/256 bytes + 8 to gain: S.region[]. Returns their number (at most 8).
-ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t ntok) {
+// Stored-region candidates come for free from the match kernel's tile flags: a 1 024-byte stretch whose flag word is zero holds
+// no match at all, so the tokens that start in it are literals. Runs of such stretches with at least ZWZ_DE_STORED_MIN tokens
+// whose byte histogram leaves a Huffman code less than n/256 bytes + 8 to gain become S.region[] (token ranges, from the marks
+// the parse left in S.kb_tok). Returns their number (at most 8).
+ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t n, uint32_t ntok) {
     EncWarpSmem &S = enc_smem();
     const unsigned lane = lane_id();
+    const uint32_t nkb = (n + 1023u) >> 10;
+    const unsigned q0 = __ballot_sync(ZWZ_FULL, lane < nkb && S.tflags[lane] == 0u);
+    const unsigned q1 = __ballot_sync(ZWZ_FULL, lane + 32u < nkb && S.tflags[lane + 32u] == 0u);
+    uint64_t quiet = (uint64_t) q0 | ((uint64_t) q1 << 32);
     uint32_t nreg = 0;
-    uint32_t run_start = 0xffffffffu;
-    for (uint32_t base = 0; base < ntok + 32u && nreg < 8u; base += 32u) { // one extra step closes a run that reaches the end
-        const uint32_t i = base + lane;
-        const bool lit = i < ntok && tok_len(m[i]) == 0u;
-        const unsigned all = __ballot_sync(ZWZ_FULL, lit || i >= ntok);
-        const bool full = base < ntok && all == ZWZ_FULL;
-        if (full) {
-            if (run_start == 0xffffffffu) run_start = base;
-            continue;
-        }
-        if (run_start != 0xffffffffu) {
-            const uint32_t r0 = run_start, r1 = base < ntok ? base : ntok;
-            run_start = 0xffffffffu;
-            if (r1 - r0 >= ZWZ_DE_STORED_MIN) {
-                enc_hist_tokens(m, r0, r1, true); // into S.code: S.freq keeps the whole-chunk histogram
-                uint32_t nu;
-                const float h_bits = enc_entropy_bits(1u, &nu);
-                const float nb = (float) (r1 - r0);
-                if (8.f * nb - h_bits < nb * (1.f / 32.f) + 64.f) {
-                    if (lane == 0) {
-                        S.region[2u * nreg] = r0;
-                        S.region[2u * nreg + 1u] = r1;
-                    }
-                    ++nreg;
+    while (quiet && nreg < 8u) { // warp-uniform
+        const uint32_t a = (uint32_t) __ffsll((long long) quiet) - 1u;
+        uint64_t rest = ~(quiet >> a); // first zero above a ends the run
+        const uint32_t len = rest ? (uint32_t) __ffsll((long long) rest) - 1u : 64u - a;
+        const uint32_t b = a + len;
+        quiet = b >= 64u ? 0ull : quiet & ~((1ull << b) - 1ull);
+        const uint32_t r0 = S.kb_tok[a], r1 = b < nkb ? S.kb_tok[b] : ntok;
+        if (r1 > r0 && r1 - r0 >= ZWZ_DE_STORED_MIN) {
+            enc_hist_tokens(m, r0, r1, true); // into S.code: S.freq keeps the whole-chunk histogram
+            uint32_t nu;
+            const float h_bits = enc_entropy_bits(1u, &nu);
+            const float nb = (float) (r1 - r0);
+            if (8.f * nb - h_bits < nb * (1.f / 32.f) + 64.f) {
+                if (lane == 0) {
+                    S.region[2u * nreg] = r0;
+                    S.region[2u * nreg + 1u] = r1;
                 }
+                ++nreg;
             }
         }
     }
@@ -700,15 +702,31 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     }
 
     // ---------------- parse ----------------
+    // A position's scratch word exists only if its 32-position tile holds a match (tile flags); the other tiles are literals
+    // straight from the raw bytes.
+    {
+        const uint32_t *gflags = m + scr_flag_offset(n);
+        S.tflags[lane] = gflags[lane];
+        S.tflags[lane + 32u] = gflags[lane + 32u];
+    }
+    __syncwarp();
+#define ENC_WORD_AT(x_) ((x_) < n ? (((S.tflags[(x_) >> 10] >> (((x_) >> 5) & 31u)) & 1u) ? m[(x_)] : ((uint32_t) src[(x_)] << 24)) : 0u)
     uint32_t ntok = 0;
-    uint32_t lit_run = 0, max_lit_run = 0; // tokens since the last match / longest such stretch (stored-region candidates)
+    uint32_t last_kb = 0xffffffffu;
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)
-    uint32_t m0 = lane < n ? m[lane] : 0u;
+    uint32_t m0 = ENC_WORD_AT(lane);
     for (uint32_t p = 0; p < n;) {
         uint32_t q = p + lane;
+        if ((p >> 10) != last_kb) { // first step inside this 1 024-byte stretch: a token boundary the stored regions can use
+            last_kb = p >> 10;
+            if (lane == 0) {
+                S.kb_tok[last_kb] = (uint16_t) ntok;
+                S.kb_pos[last_kb] = (uint16_t) p;
+            }
+        }
         // the window after this one, fetched before it is known to be needed: when the window holds no match that leaves
         // it (J0 == 32: every literal-only stretch) the next step starts without waiting on a dependent load
-        const uint32_t mnx = q + 32u < n ? m[q + 32u] : 0u;
+        const uint32_t mnx = ENC_WORD_AT(q + 32u);
         uint32_t m1 = __shfl_down_sync(ZWZ_FULL, m0, 1);
         const uint32_t mfirst = __shfl_sync(ZWZ_FULL, mnx, 0);
         if (lane == 31u) m1 = mfirst;
@@ -748,16 +766,11 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
             m[ntok + (uint32_t) __popc(tm & ((1u << lane) - 1u))] = tok;
         }
         ntok += (uint32_t) __popc(tm);
-        if (__ballot_sync(ZWZ_FULL, marked && take)) {
-            max_lit_run = lit_run > max_lit_run ? lit_run : max_lit_run;
-            lit_run = 0;
-        } else {
-            lit_run += (uint32_t) __popc(tm);
-        }
         p += J0;
         if (J0 == 32u) m0 = mnx;
-        else m0 = p + lane < n ? m[p + lane] : 0u;
+        else m0 = ENC_WORD_AT(p + lane);
     }
+#undef ENC_WORD_AT
     if (lane == 0) S.freq[256] += 1u; // end of block
     extra_bits = warp_sum64(extra_bits);
     __syncwarp();
@@ -820,8 +833,8 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     BitSink k;
     sink_init(S, k, (uint32_t *) out, cap_words);
     sink_put(S, k, lane == 0 ? 0x9c78ull : 0ull, lane == 0 ? 16u : 0u); // RFC 1950 header 78 9C
-    max_lit_run = lit_run > max_lit_run ? lit_run : max_lit_run;
-    const uint32_t nreg = max_lit_run >= ZWZ_DE_STORED_MIN ? enc_find_stored_regions(m, ntok) : 0u;
+    __syncwarp();
+    const uint32_t nreg = enc_find_stored_regions(m, n, ntok);
     if (nreg == 0u) {
         enc_emit_range(&k, m, 0, ntok, extra_bits, true, true); // S.freq still holds the whole-chunk histogram from the parse
     } else {

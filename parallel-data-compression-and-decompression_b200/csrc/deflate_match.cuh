@@ -73,7 +73,7 @@ static_assert(2u * (MatchClass<2>::kSmem + 1024u) <= 228u * 1024u && 3u * (Match
 
 // scratch layout of one chunk (uint32 units): [0, A) best match per position, then tokens in place (deflate_encode.cuh);
 // [A, A + B) the hash-partitioned position lists (u16) used only inside lz_match_kernel
-ZWZ_DEV uint32_t dm_scratch_match_words(uint32_t n) { return (n + 2u + 31u) & ~31u; }
+ZWZ_DEV uint32_t dm_scratch_match_words(uint32_t n) { return scr_match_words(n); }
 
 template <int HBITS> ZWZ_DEV uint32_t dm_hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
     uint32_t v = b0 | (b1 << 8) | (b2 << 16);
@@ -276,6 +276,16 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             }
         }
         __syncthreads();
+        // The lists are dead now. They were written and read back through L2 by this CTA alone: tell L2 to drop the lines instead
+        // of writing 2 bytes per input byte back to DRAM (profiles/round1: lz_match moved 6.9x its algorithmic bytes).
+        {
+            const uint32_t list_lines = (nhash * 2u + 127u) >> 7;
+            for (uint32_t i = tid; i < list_lines; i += T) discard_l2_line((const unsigned char *) list + 128u * i);
+        }
+        // tile flags of this chunk, collected in the (now free) cnt area: bit t = tile t holds a match
+        uint32_t *tflags = (uint32_t *) cnt;
+        for (uint32_t i = tid; i < ZWZ_SCR_FLAG_WORDS && i < NW * NW / 2u; i += T) tflags[i] = 0u;
+        __syncthreads();
 
         // ---- 6. search: one lane per position, 32-position tiles ----
         for (;;) {
@@ -324,11 +334,22 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 }
                 if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             }
-            if (p < n) mout[p] = tok_make(lds8(sD + p), best_len >= 3u ? best_len : 0u, best_dist);
+            // a tile without a single match is not written at all: the encoder takes its literals from the raw bytes
             const unsigned hit = __ballot_sync(ZWZ_FULL, best_len >= 3u);
-            if (lane == 0 && hit) atomicAdd(&ctl->nmatch, (uint32_t) __popc(hit));
+            if (hit) {
+                if (p < n) mout[p] = tok_make(lds8(sD + p), best_len >= 3u ? best_len : 0u, best_dist);
+                if (lane == 0) {
+                    atomicAdd(&ctl->nmatch, (uint32_t) __popc(hit));
+                    atomicOr(&tflags[tile >> 5], 1u << (tile & 31u));
+                }
+            }
         }
         __syncthreads();
+        {
+            uint32_t *gflags = mout + scr_flag_offset(n);
+            const uint32_t used = (ntiles + 31u) >> 5;
+            for (uint32_t i = tid; i < ZWZ_SCR_FLAG_WORDS; i += T) gflags[i] = i < used ? tflags[i] : 0u;
+        }
 
         // ---- 7. Adler-32 of the chunk ----
         {

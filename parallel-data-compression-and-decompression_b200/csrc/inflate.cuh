@@ -23,7 +23,7 @@
 
 namespace zwz {
 
-#define ZWZ_INF_WARPS 4
+#define ZWZ_INF_WARPS 1 // one warp per CTA: ~14 KB of shared memory each, so the CTA count per SM is what shared memory allows
 #define ZWZ_INF_LBITS 10
 #define ZWZ_INF_DBITS 8
 
@@ -43,12 +43,16 @@ struct InflateWarpSmem {
     uint32_t cnt_ll[16];
     uint32_t cnt_d[16];
     uint32_t run[16]; // running offsets while sorting
-    uint8_t lens[352]; // [0,19) code-length-code lengths; [32, 32+316) literal/length then distance lengths
-    uint32_t clt[128]; // code-length-code table (7 bits)
-    uint16_t sorted_cl[20];
-    uint32_t cnt_cl[16];
-    uint32_t cw[32u * 15u + 8u];  // inflate_fast.cuh: staged window of compressed words (ZWZ_IF_CW)
-    uint16_t tok[32u * 130u];     // inflate_fast.cuh: one token region per lane (32 x ZWZ_IF_RS)
+    uint32_t cw[32u * 15u + 8u];  // inflate_fast.cuh: staged window of compressed words (ZWZ_IF_CW), then the resolve staging area
+    union {
+        struct { // block header parsing only: dead once the tables are built, when the token regions come to life
+            uint8_t lens[352]; // [0,19) code-length-code lengths; [32, 32+316) literal/length then distance lengths
+            uint32_t clt[128]; // code-length-code table (7 bits)
+            uint16_t sorted_cl[20];
+            uint32_t cnt_cl[16];
+        };
+        uint16_t tok[32u * 98u];  // inflate_fast.cuh: one token region per lane (32 x ZWZ_IF_RS)
+    };
 };
 #define ZWZ_INF_SMEM (ZWZ_INF_WARPS * (uint32_t) sizeof(zwz::InflateWarpSmem))
 

@@ -25,9 +25,10 @@ namespace zwz {
 #define ZWZ_IF_SW 15u                          // words of compressed data per lane and window
 #define ZWZ_IF_SBITS (ZWZ_IF_SW * 32u)         // 480 bits: longer than any token (48 bits), 15 is odd -> conflict-free strides
 #define ZWZ_IF_CW (32u * ZWZ_IF_SW + 8u)       // staged words: 32 ranges + the overshoot of the last token
-#define ZWZ_IF_R 128u                          // token entries (u16) a lane may emit per window
-#define ZWZ_IF_RS 130u                         // region stride in u16: 65 words, so equal offsets in 32 regions hit 32 banks
+#define ZWZ_IF_R 96u                           // token entries (u16) a lane may emit per window
+#define ZWZ_IF_RS 98u                          // region stride in u16: 49 words (odd), so equal offsets in 32 regions hit 32 banks
 #define ZWZ_IF_MAXIT 6                         // rounds per window; then the proven prefix is committed and a new window starts
+#define ZWZ_IF_STG 1536u                       // output bytes assembled per resolve step (lives in the staged-window area)
 
 #ifdef ZWZ_EMU
 // test-only counters of the emulator build: [0] windows, [1] decode rounds, [2] committed lanes, [3] token entries,
@@ -97,85 +98,70 @@ ZWZ_DEV int inf_fast_block(SMEM &S, const BITS &B, uint64_t &bitpos, uint32_t ma
         __syncwarp();
 
         // ---- decode: rounds until the lanes agree ----
+        // The token loop is ONE instruction stream for all lanes (warp-uniform trip count, literal and match handled by the same
+        // straight-line code with selects): a loop in which every lane branches on its own symbol kind lets the lanes drift apart
+        // and the warp then executes each lane's iterations separately (measured: 5x the instructions).
         const uint32_t hi = base_bit + (lane + 1u) * ZWZ_IF_SBITS;
         uint32_t start = base_bit + lane * ZWZ_IF_SBITS;
         uint32_t e = 0, ntok = 0, flag = IFL_RUN;
         bool need = true;
         uint32_t ncommit = 0;
         for (int it = 0;; ++it) {
+            uint32_t p = start;
+            bool run = need;
             if (need) {
-                uint32_t p = start;
                 ntok = 0;
                 flag = IFL_RUN;
-                while (p < hi) {
-                    if (ntok + 2u > ZWZ_IF_R) {
-                        flag = IFL_FULL;
-                        break;
-                    }
+            }
+            while (__any_sync(ZWZ_FULL, run)) {
+                ZWZ_IF_STAT(7, 1);
+                if (run) {
                     const uint32_t bits = iff_fetch(S.cw, p);
                     uint32_t en = S.lit[bits & ((1u << ZWZ_INF_LBITS) - 1u)];
-                    uint32_t kind = (en >> 8) & 3u;
-                    if (kind == INF_KIND_SPECIAL) {
-                        if ((en >> 4) & 15u) { // code longer than the table index
-                            uint32_t len = 0;
-                            const uint32_t sym = inf_canon_walk(bits, S.cnt_ll, S.sorted_ll, max_ll, len);
-                            en = sym == 0xffffffffu ? ZWZ_INF_INVALID(max_ll) : inf_litlen_entry(sym, len);
-                            kind = (en >> 8) & 3u;
-                        }
-                        if (kind == INF_KIND_SPECIAL) {
-                            flag = IFL_STOP;
-                            break;
-                        }
+                    if (((en >> 8) & 3u) == INF_KIND_SPECIAL && ((en >> 4) & 15u)) { // code longer than the table index (rare)
+                        uint32_t len = 0;
+                        const uint32_t sym = inf_canon_walk(bits, S.cnt_ll, S.sorted_ll, max_ll, len);
+                        en = sym == 0xffffffffu ? ZWZ_INF_INVALID(max_ll) : inf_litlen_entry(sym, len);
                     }
-                    const uint32_t nb = en & 15u;
-                    if (kind == INF_KIND_LIT) {
-                        if (p + nb > limit) {
-                            flag = IFL_STOP;
-                            break;
-                        }
-                        my[ntok++] = (uint16_t) (en >> 16);
-                        p += nb;
-                        continue;
-                    }
-                    if (kind == INF_KIND_EOB) {
-                        if (p + nb > limit) {
-                            flag = IFL_STOP;
-                            break;
-                        }
-                        p += nb;
-                        flag = IFL_EOB;
-                        break;
-                    }
-                    const uint32_t eb = (en >> 4) & 15u;
-                    const uint32_t mlen = (en >> 16) + ((bits >> nb) & ((1u << eb) - 1u));
-                    uint32_t p2 = p + nb + eb;
+                    const uint32_t kind = (en >> 8) & 3u;
+                    const uint32_t nb = en & 15u, eb = (en >> 4) & 15u;
+                    const uint32_t val = (en >> 16) + ((bits >> nb) & ((1u << eb) - 1u)); // literal byte, or match length (eb = 0 for literals)
+                    const uint32_t p2 = p + nb + eb;
+                    // the distance code behind a length code; decoded for every lane, used by the lanes that hold a length
                     const uint32_t bits2 = iff_fetch(S.cw, p2);
                     uint32_t d = S.dst[bits2 & ((1u << ZWZ_INF_DBITS) - 1u)];
-                    if (((d >> 8) & 3u) == INF_KIND_SPECIAL) {
-                        if ((d >> 4) & 15u) {
-                            uint32_t len = 0;
-                            const uint32_t sym = inf_canon_walk(bits2, S.cnt_d, S.sorted_d, max_d, len);
-                            d = sym == 0xffffffffu ? ZWZ_INF_INVALID(max_d) : inf_dist_entry(sym, len);
-                        }
-                        if (((d >> 8) & 3u) == INF_KIND_SPECIAL) {
-                            flag = IFL_STOP;
-                            break;
-                        }
+                    const bool is_len = kind == INF_KIND_BASE;
+                    if (is_len && ((d >> 8) & 3u) == INF_KIND_SPECIAL && ((d >> 4) & 15u)) {
+                        uint32_t len = 0;
+                        const uint32_t sym = inf_canon_walk(bits2, S.cnt_d, S.sorted_d, max_d, len);
+                        d = sym == 0xffffffffu ? ZWZ_INF_INVALID(max_d) : inf_dist_entry(sym, len);
                     }
                     const uint32_t dnb = d & 15u, deb = (d >> 4) & 15u;
                     const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << deb) - 1u));
-                    p2 += dnb + deb;
-                    if (p2 > limit) {
+                    const uint32_t pn = is_len ? p2 + dnb + deb : p2;
+                    const bool bad = kind == INF_KIND_SPECIAL || (is_len && ((d >> 8) & 3u) == INF_KIND_SPECIAL) || pn > limit;
+                    if (bad) { // invalid code, or a token that does not lie completely inside the input: the careful decoder's business
                         flag = IFL_STOP;
-                        break;
+                        run = false;
+                    } else if (kind == INF_KIND_EOB) {
+                        p = pn;
+                        flag = IFL_EOB;
+                        run = false;
+                    } else {
+                        my[ntok] = (uint16_t) (is_len ? (0x8000u | val) : val);
+                        if (is_len) my[ntok + 1u] = (uint16_t) (dist - 1u);
+                        ntok += is_len ? 2u : 1u;
+                        p = pn;
+                        if (p >= hi) {
+                            run = false;
+                        } else if (ntok + 2u > ZWZ_IF_R) {
+                            flag = IFL_FULL;
+                            run = false;
+                        }
                     }
-                    my[ntok] = (uint16_t) (0x8000u | mlen);
-                    my[ntok + 1u] = (uint16_t) (dist - 1u);
-                    ntok += 2u;
-                    p = p2;
                 }
-                e = p;
             }
+            if (need) e = p;
             __syncwarp();
             const uint32_t pe = __shfl_up_sync(ZWZ_FULL, e, 1);
             const uint32_t pf = __shfl_up_sync(ZWZ_FULL, flag, 1);
@@ -198,11 +184,16 @@ ZWZ_DEV int inf_fast_block(SMEM &S, const BITS &B, uint64_t &bitpos, uint32_t ma
             if (need) start = pe;
         }
 
-        // ---- resolve: replay the proven regions in order ----
+        // ---- resolve: replay the proven regions in order, <= 32 token entries per step ----
+        // Output of a step is assembled in shared memory (the staged window is dead by now) and then written out in one go.
+        // Every output byte of the step is produced by its own lane: the token that covers it is found by a binary search over
+        // the step's running lengths, bytes whose source lies before the step come from global memory — all loads of the step
+        // are independent, so their latency overlaps — and only matches that reach into the step's own output wait for it.
         ZWZ_IF_STAT(0, 1);
         ZWZ_IF_STAT(2, ncommit);
         const uint32_t last_flag = __shfl_sync(ZWZ_FULL, flag, (int) (ncommit - 1u));
         const uint32_t last_e = __shfl_sync(ZWZ_FULL, e, (int) (ncommit - 1u));
+        uint8_t *const stg = (uint8_t *) S.cw;
         for (uint32_t l = 0; l < ncommit; ++l) {
             const uint32_t nl = __shfl_sync(ZWZ_FULL, ntok, (int) l);
             ZWZ_IF_STAT(3, nl);
@@ -212,47 +203,90 @@ ZWZ_DEV int inf_fast_block(SMEM &S, const BITS &B, uint64_t &bitpos, uint32_t ma
                 const uint32_t idx = j0 + lane;
                 uint32_t t = idx < nl ? (uint32_t) reg[idx] : 0u;
                 unsigned hm = __ballot_sync(ZWZ_FULL, (t & 0x8000u) != 0u);
-                uint32_t take = 32u;
+                uint32_t take = nl - j0 < 32u ? nl - j0 : 32u;
                 if (hm >> 31) { // a match head in the last lane: its distance entry belongs to the next step
                     take = 31u;
                     hm &= 0x7fffffffu;
                     if (lane == 31u) t = 0u;
                 }
-                const uint32_t nvalid = nl - j0 < take ? nl - j0 : take;
                 if (hm == 0u) { // literals only
                     const uint32_t q = pos + lane;
-                    if (lane < nvalid && q < cap) out[q] = (uint8_t) t;
-                    if (pos + nvalid > cap) overflow = true;
-                    pos += nvalid;
-                } else {
-                    const bool is_head = (hm >> lane) & 1u;
-                    const bool is_dist = lane > 0u && ((hm >> (lane - 1u)) & 1u);
-                    const uint32_t olen = lane >= nvalid || is_dist ? 0u : (is_head ? (t & 0x1ffu) : 1u);
-                    const uint32_t incl = warp_incl_scan(olen);
-                    const uint32_t excl = incl - olen;
-                    const uint32_t total = __shfl_sync(ZWZ_FULL, incl, 31);
-                    const uint32_t dn = __shfl_down_sync(ZWZ_FULL, t, 1); // distance entry of a head lane
-                    if (olen == 1u && !is_head) {
-                        const uint32_t q = pos + excl;
-                        if (q < cap) out[q] = (uint8_t) t;
+                    if (lane < take && q < cap) out[q] = (uint8_t) t;
+                    if (pos + take > cap) overflow = true;
+                    pos += take;
+                    j0 += take;
+                    continue;
+                }
+                const bool is_head = (hm >> lane) & 1u;
+                const bool is_dist = lane > 0u && ((hm >> (lane - 1u)) & 1u);
+                uint32_t olen = lane >= take || is_dist ? 0u : (is_head ? (t & 0x1ffu) : 1u);
+                uint32_t incl = warp_incl_scan(olen);
+                // a step's output must fit the staging area: cut behind the last entry that still does
+                const unsigned fits = __ballot_sync(ZWZ_FULL, incl <= ZWZ_IF_STG);
+                if (fits != ZWZ_FULL) {
+                    take = (uint32_t) __ffs((int) ~fits) - 1u; // >= 3: a token is at most 258 bytes
+                    if (lane >= take) olen = 0u;
+                    hm &= (1u << take) - 1u;
+                    incl = warp_incl_scan(olen);
+                }
+                const uint32_t excl = incl - olen;
+                const uint32_t total = __shfl_sync(ZWZ_FULL, incl, 31);
+                const uint32_t dn = __shfl_down_sync(ZWZ_FULL, t, 1); // distance - 1 of a head lane
+                // invalid distance too far back: zlib stops at the first such match with everything before it written
+                const unsigned far = __ballot_sync(ZWZ_FULL, is_head && lane < take && dn + 1u > pos + excl);
+                // matches that reach into this step's own output (source position + min(len, dist) > step start)
+                const unsigned deps = __ballot_sync(ZWZ_FULL, is_head && lane < take && excl + (olen < dn + 1u ? olen : dn + 1u) > dn + 1u);
+                // ---- every byte of the step by its own lane ----
+                for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
+                    const uint32_t b = b0 + lane;
+                    uint32_t j = 0;
+#pragma unroll
+                    for (uint32_t sft = 16u; sft != 0u; sft >>= 1) {
+                        const uint32_t v = __shfl_sync(ZWZ_FULL, incl, (int) (j + sft - 1u));
+                        if (v <= b) j += sft;
+                    }
+                    j &= 31u; // lanes past `total` search past the end
+                    const uint32_t tj = __shfl_sync(ZWZ_FULL, t, (int) j);
+                    const uint32_t ej = __shfl_sync(ZWZ_FULL, excl, (int) j);
+                    const uint32_t dj = __shfl_sync(ZWZ_FULL, dn, (int) j) + 1u;
+                    if (b < total) {
+                        if ((hm >> j) & 1u) {
+                            const uint32_t i = b - ej;                                                // byte i of the match
+                            const uint32_t src = ej + (dj >= (tj & 0x1ffu) || i < dj ? i : i % dj);   // its source + dist, relative to the step
+                            // before the step iff src < dj; a too-far match (dj > pos + ej) is never written out: skip its loads
+                            if (src < dj && dj <= pos + ej) stg[b] = __ldcg(out + (pos + src - dj));
+                        } else {
+                            stg[b] = (uint8_t) tj;
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- matches that read this step's own output, in order (their sources lie in EARLIER tokens of the step) ----
+                unsigned m = deps & hm;
+                if (far) m &= (far & (0u - far)) - 1u; // nothing at or behind the first too-far match is produced
+                while (m) {
+                    const int j = __ffs((int) m) - 1;
+                    m &= m - 1u;
+                    const uint32_t mlen = __shfl_sync(ZWZ_FULL, olen, j);
+                    const uint32_t m0 = __shfl_sync(ZWZ_FULL, excl, j);
+                    const uint32_t dist = __shfl_sync(ZWZ_FULL, dn, j) + 1u;
+                    for (uint32_t i = lane; i < mlen; i += 32u) {
+                        const uint32_t src = m0 + (dist >= mlen || i < dist ? i : i % dist);
+                        if (src >= dist) stg[m0 + i] = stg[src - dist];
                     }
                     __syncwarp();
-                    unsigned m = hm;
-                    while (m) { // warp-uniform: one match at a time, in order
-                        const int j = __ffs((int) m) - 1;
-                        m &= m - 1u;
-                        const uint32_t mlen = __shfl_sync(ZWZ_FULL, olen, j);
-                        const uint32_t mpos = pos + __shfl_sync(ZWZ_FULL, excl, j);
-                        const uint32_t dist = __shfl_sync(ZWZ_FULL, dn, j) + 1u;
-                        if (dist > mpos) { // "invalid distance too far back": zlib stops here with everything before it written
-                            pos = mpos;
-                            return IFR_BAD;
-                        }
-                        inf_copy_match(out, mpos, mlen, dist, cap);
-                    }
-                    if (pos + total > cap) overflow = true;
-                    pos += total;
                 }
+                // ---- write the step out ----
+                uint32_t wr = total;
+                if (far) wr = __shfl_sync(ZWZ_FULL, excl, __ffs((int) far) - 1);
+                for (uint32_t b = lane; b < wr; b += 32u) {
+                    const uint32_t q = pos + b;
+                    if (q < cap) out[q] = stg[b];
+                }
+                if (pos + wr > cap) overflow = true;
+                pos += wr;
+                if (far) return IFR_BAD;
+                __syncwarp();
                 j0 += take;
             }
         }

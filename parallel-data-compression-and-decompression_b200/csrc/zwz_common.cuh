@@ -140,9 +140,22 @@ ZWZ_DEV uint32_t tok_dist(uint32_t t) { return (t & 0x7fffu) + 1u; }
 ZWZ_DEV uint32_t tok_byte(uint32_t t) { return t >> 24; }
 #ifdef ZWZ_EMU
 ZWZ_DEV void prefetch_l2(const void *) {}
+ZWZ_DEV void discard_l2_line(const void *) {}
 #else
 ZWZ_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// The 128-byte line at p (128-byte aligned) holds dead data: drop it from L2 WITHOUT writing it back to DRAM.
+ZWZ_DEV void discard_l2_line(const void *p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 #endif
+
+// ---- scratch layout of one chunk of n raw bytes (uint32 units from job.scr_off[c]; keep in step with zwz_cuda.cu) --------
+//   [0, A)          best match per position (lz_match_kernel) — only the 32-position tiles that HOLD a match are written —
+//                   overwritten in place by the parser with the token stream (deflate_encode_kernel)
+//   [A, A + B)      the hash-partitioned u16 position lists of lz_match_kernel (dead, and discarded from L2, once the chains exist)
+//   [A + B, +64)    one bit per 32-position tile: the tile holds at least one match (its words in [0, A) are valid)
+#define ZWZ_SCR_FLAG_WORDS 64u
+ZWZ_DEV uint32_t scr_match_words(uint32_t n) { return (n + 2u + 31u) & ~31u; }
+ZWZ_DEV uint32_t scr_list_words(uint32_t n) { return ((n + 1u) / 2u + 32u + 31u) & ~31u; }
+ZWZ_DEV uint32_t scr_flag_offset(uint32_t n) { return scr_match_words(n) + scr_list_words(n); }
 
 // ---- DEFLATE symbol arithmetic (RFC 1951 §3.2.5) without tables ----------------------------------------------------
 // length 3..258 -> (symbol 257..285, extra bit count, extra value)

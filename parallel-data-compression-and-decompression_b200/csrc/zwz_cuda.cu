@@ -438,7 +438,7 @@ int zwz_deflate_batch_device(zwz_ctx *ctx, const uint8_t *d_raw, const uint64_t 
             h_len[i] = len[i];
             // uint32 entries: best match per position (+ pad so the parser may peek one past the end), then the u16 position
             // lists of lz_match_kernel (deflate_match.cuh: dm_scratch_match_words)
-            scr += align_up((size_t) len[i] + 2, 32) + align_up(((size_t) len[i] + 1) / 2 + 32, 32);
+            scr += align_up((size_t) len[i] + 2, 32) + align_up(((size_t) len[i] + 1) / 2 + 32, 32) + ZWZ_SCR_FLAG_WORDS; // zwz_common.cuh: scratch layout
             raw += len[i];
         }
         max_scr = std::max(max_scr, scr);
@@ -756,7 +756,7 @@ int zwz_inflate_batch_device(zwz_ctx *ctx, const uint8_t *d_comp, const uint64_t
                        (const uint32_t *) (dm + m_len), d_raw_out, (const uint64_t *) (dm + m_roff), d_rlen, d_stat,
                        (const uint32_t *) (dm + m_order), n, flags, d_counter);
         } else {
-            const uint32_t per_sm = std::max<uint32_t>(1u, (uint32_t) ((228u * 1024u) / (ZWZ_INF_SMEM + 1024u)));
+            const uint32_t per_sm = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (uint32_t) ((228u * 1024u) / (ZWZ_INF_SMEM + 1024u))));
             uint32_t grid = std::min<uint32_t>((n + ZWZ_INF_WARPS - 1) / ZWZ_INF_WARPS, (uint32_t) ctx->sm_count * per_sm);
             if (ctx->inflate_mode == 3) flags |= ZWZ_INFLATE_CAREFUL;
             ZWZ_LAUNCH(zwz::inflate_kernel, grid, ZWZ_INF_WARPS * 32, ZWZ_INF_SMEM, st, d_comp, (const uint64_t *) (dm + m_off),

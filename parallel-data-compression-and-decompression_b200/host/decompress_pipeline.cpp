@@ -20,12 +20,15 @@
 #include "pipeline.hpp"
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
 #include <fstream>
 #include <iostream>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <unordered_map>
 #include <sstream>
 #include <sys/mman.h>
@@ -70,7 +73,9 @@ struct Archive {
 struct Group {
     size_t archive = 0, first = 0, count = 0; // files [first, first + count) of that archive
     size_t nrec = 0;
-    bool big = false; // one file whose records exceed a batch: streamed through in sub-batches
+    bool segment = false;  // records [r0, r1) of ONE file whose records exceed a batch
+    size_t r0 = 0, r1 = 0;
+    int big = -1, seg = 0; // index into the big-file table, segment number inside the file
 };
 
 // decompression.cpp:65-92
@@ -154,8 +159,34 @@ void parse_archive(const Span &a, std::vector<FileState> &files) {
 }
 
 
-// `last_dir` remembers the directory of the previous call (files of one directory are consecutive in an archive): one
-// existence check per directory instead of one per file
+// console text of one group
+struct Console {
+    std::ostringstream out, err;
+};
+
+// Console lines leave the process in group order whatever the workers' timing: a finished group posts its text, and whoever
+// posts prints every consecutive group that is ready. Nobody ever waits here.
+class OrderedConsole {
+  public:
+    void post(size_t g, std::string out, std::string err) {
+        std::lock_guard<std::mutex> lock(mu_);
+        ready_[g] = {std::move(out), std::move(err)};
+        for (auto it = ready_.find(next_); it != ready_.end(); it = ready_.find(next_)) {
+            if (!it->second.first.empty()) std::cout << it->second.first << std::flush;
+            if (!it->second.second.empty()) std::cerr << it->second.second << std::flush;
+            ready_.erase(it);
+            ++next_;
+        }
+    }
+    void skip(size_t g) { post(g, "", ""); } // a group that belongs to another rank
+
+  private:
+    std::mutex mu_;
+    std::map<size_t, std::pair<std::string, std::string>> ready_;
+    size_t next_ = 0;
+};
+
+// one directory-existence check per directory instead of one per file (files of a directory are consecutive in an archive)
 void ensure_parent(const std::string &file_path, std::string &last_dir) {
     const size_t slash = file_path.find_last_of('/');
     if (slash == std::string::npos || slash == 0) return;
@@ -165,17 +196,23 @@ void ensure_parent(const std::string &file_path, std::string &last_dir) {
     if (!fs::exists(last_dir, ec)) fs::create_directories(last_dir, ec);
 }
 
-// console text of one group, released in group order
-struct Console {
-    std::ostringstream out, err;
-};
-
-void print_verdict(Console &con, RunStats &st, const std::string &file_path, const std::string &stored, const std::string &calculated) {
-    if (calculated != stored) { // decompression.cpp:140-146
+// decompression.cpp:140-146, plus the quarantine the reference's README promises (README.md:175,186) behind ZWZ_QUARANTINE=1:
+// a file whose MD5 does not match is moved to <output dir>/bad/<relative path>
+void print_verdict(Console &con, RunStats &st, const std::string &output_dir, const std::string &relpath, const std::string &stored,
+                   const std::string &calculated) {
+    const std::string file_path = output_dir + "/" + relpath;
+    if (calculated != stored) {
         con.err << "MD5 mismatch for file: " << file_path << "\n";
         con.out << "Expected MD5: " << stored << "\n";
         con.out << "Calculated MD5: " << calculated << "\n";
         st.md5_mismatch++;
+        if (config().quarantine) {
+            const std::string bad = output_dir + "/bad/" + relpath;
+            std::error_code ec;
+            fs::create_directories(fs::path(bad).parent_path(), ec);
+            fs::rename(file_path, bad, ec);
+            if (!ec) con.err << "Moved to: " << bad << "\n";
+        }
     } else {
         con.out << "MD5 match for file: " << file_path << "\n";
         st.md5_match++;
@@ -204,27 +241,96 @@ void merge_stats(const RunStats &s) {
     g.t_write += s.t_write;
 }
 
+void write_all_at(int fd, const uint8_t *p, size_t n, uint64_t off) {
+    while (n) {
+        ssize_t w = ::pwrite(fd, p, n, (off_t) off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw std::runtime_error("zwz: short write to an output file");
+        }
+        p += w;
+        n -= (size_t) w;
+        off += (uint64_t) w;
+    }
+}
+
+// A file whose records exceed a batch is cut into SEGMENTS of consecutive records that workers — of this rank, or of several
+// ranks — inflate independently. A segment's place in the output file is the sum of the raw sizes of the segments before it,
+// known only once those are inflated: the ledger hands out offsets in segment order. Inside one process it is a counter
+// behind a condition variable; across ranks (ZWZ_GPUS=N decompress) the raw size of every finished segment is published as a
+// tiny file under <output dir>/.zwz_segments/ and read by the ranks that need it (the same shared-directory channel the
+// compress side uses for the file record; the reference format itself has no index to exchange).
+struct BigOut {
+    size_t archive = 0, file = 0;
+    int nseg = 0;
+    std::string path;   // output file
+    std::string key;    // ledger key across ranks
+    std::mutex mu;
+    std::condition_variable cv;
+    int next_seg = 0;          // single process: segments [0, next_seg) have their sizes in
+    uint64_t next_off = 0;
+    std::atomic<int> written{0};
+    std::atomic<uint64_t> bad{0};
+};
+
 struct Job {
     std::vector<Archive> &archives;
     const std::vector<Group> &groups;
+    std::vector<std::unique_ptr<BigOut>> &bigs;
     const std::string &output_dir;
     uint64_t budget;
     int device;
+    int rank, world;
     size_t max_comp = 0, max_out = 0; // of any planned group: page-locked buffers are sized once per worker
     std::atomic<size_t> next_group{0};
-    OrderedCommit order;
-    Job(std::vector<Archive> &a, const std::vector<Group> &g, const std::string &out, uint64_t budget_, int device_)
-        : archives(a), groups(g), output_dir(out), budget(budget_), device(device_) {
+    OrderedConsole console;
+    OrderedCommit abort_only; // run_workers wants one; nothing waits on it here
+    Job(std::vector<Archive> &a, const std::vector<Group> &g, std::vector<std::unique_ptr<BigOut>> &b, const std::string &out, uint64_t budget_,
+        int device_, int rank_, int world_)
+        : archives(a), groups(g), bigs(b), output_dir(out), budget(budget_), device(device_), rank(rank_), world(world_) {
         for (const auto &x : g) {
-            if (x.big) continue;
             size_t comp = 0;
-            for (size_t f = x.first; f < x.first + x.count; ++f)
-                for (const auto &r : a[x.archive].files[f].ordered) comp += r.len;
+            if (x.segment) {
+                const auto &recs = a[x.archive].files[x.first].ordered;
+                for (size_t r = x.r0; r < x.r1; ++r) comp += recs[r].len;
+            } else {
+                for (size_t f = x.first; f < x.first + x.count; ++f)
+                    for (const auto &r : a[x.archive].files[f].ordered) comp += r.len;
+            }
             max_comp = std::max(max_comp, comp);
             max_out = std::max(max_out, x.nrec * CHUNK_SIZE);
         }
     }
+    bool mine(size_t g) const { return world <= 1 || (int) (g % (size_t) world) == rank; }
 };
+
+std::string ledger_dir(const std::string &output_dir) { return output_dir + "/.zwz_segments"; }
+
+// raw size of segment `seg` of file `key`, published by whichever rank inflated it
+void ledger_publish(const std::string &output_dir, const std::string &key, int seg, const char *what, uint64_t value) {
+    const std::string final_name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
+    const std::string tmp = final_name + ".tmp" + std::to_string((long) getpid());
+    std::FILE *f = std::fopen(tmp.c_str(), "wb");
+    if (!f) throw std::runtime_error("zwz: cannot write the segment ledger");
+    std::fwrite(&value, 8, 1, f);
+    std::fclose(f);
+    if (std::rename(tmp.c_str(), final_name.c_str()) != 0) throw std::runtime_error("zwz: cannot publish to the segment ledger");
+}
+uint64_t ledger_wait(const std::string &output_dir, const std::string &key, int seg, const char *what) {
+    const std::string name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
+    const double t0 = now_seconds();
+    for (;;) {
+        std::FILE *f = std::fopen(name.c_str(), "rb");
+        if (f) {
+            uint64_t v = 0;
+            size_t k = std::fread(&v, 8, 1, f);
+            std::fclose(f);
+            if (k == 1) return v;
+        }
+        if (now_seconds() - t0 > 900.0) throw std::runtime_error("zwz: timed out waiting for segment " + std::to_string(seg) + " of " + key + " from another rank");
+        usleep(500);
+    }
+}
 
 class Worker {
   public:
@@ -232,35 +338,79 @@ class Worker {
 
     void run() {
         for (;;) {
-            size_t g = job_.next_group.fetch_add(1);
-            if (g >= job_.groups.size()) return;
+            Pending &p = pend_[turn_++ & 1];
+            finalize(p); // before a group is taken: the verdicts of two groups ago
+            size_t g;
+            for (;;) { // groups are dealt over the ranks; every rank walks the whole list
+                g = job_.next_group.fetch_add(1);
+                if (g >= job_.groups.size() || job_.mine(g)) break;
+                job_.console.skip(g);
+            }
+            if (g >= job_.groups.size()) break;
             const Group &grp = job_.groups[g];
-            Console con;
-            RunStats st;
-            if (grp.big)
-                big_file(job_.archives[grp.archive], job_.archives[grp.archive].files[grp.first], con, st);
+            p.g = g;
+            if (grp.segment)
+                segment(grp, p);
             else
-                small_files(grp, con, st);
-            job_.order.wait_turn(g);
-            std::string o = con.out.str(), e = con.err.str();
-            if (!o.empty()) std::cout << o << std::flush;
-            if (!e.empty()) std::cerr << e << std::flush;
-            job_.order.done(g);
-            merge_stats(st);
+                small_files(grp, p);
         }
+        finalize(pend_[turn_ & 1]);
+        finalize(pend_[(turn_ + 1) & 1]);
     }
 
   private:
+    struct OutFile {
+        FileState *fsx;
+        uint64_t bytes;
+        bool created;
+    };
+    // a group whose files are on disk, waiting for its digests to say what the console gets
+    struct Pending {
+        bool active = false;
+        uint64_t ticket = 0;
+        size_t g = 0;
+        Console con;
+        RunStats st;
+        std::vector<uint8_t> digest;
+        std::vector<OutFile> files;
+    };
+
+    void finalize(Pending &p) {
+        if (!p.active) return;
+        p.active = false;
+        double t0 = now_seconds();
+        if (p.ticket && zwz_wait(ctx_, p.ticket) != ZWZ_OK) throw std::runtime_error(std::string("zwz_wait: ") + zwz_last_error(ctx_));
+        p.st.t_gpu += now_seconds() - t0;
+        const RunConfig &cfg = config();
+        for (size_t i = 0; i < p.files.size(); ++i) {
+            FileState &fsx = *p.files[i].fsx;
+            if (!p.files[i].created) continue;
+            if (fsx.recs.size() != fsx.ordered.size()) p.con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
+            if (cfg.verbose && !fsx.stored_md5.empty()) p.con.out << "Read MD5: " << fsx.stored_md5 << "\n"; // decompression.cpp:90
+            if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all)) {
+                char hex[32];
+                zwz_md5_hex(&p.digest[i * 16], hex);
+                print_verdict(p.con, p.st, job_.output_dir, fsx.relpath, fsx.stored_md5, std::string(hex, 32));
+            }
+        }
+        job_.console.post(p.g, p.con.out.str(), p.con.err.str());
+        merge_stats(p.st);
+        p.con = Console();
+        p.st = RunStats();
+        p.files.clear();
+        p.ticket = 0;
+    }
+
     // Records whose stream did not reach a clean end (truncated, invalid, checksum mismatch). Counted always; named on stderr
     // only with ZWZ_STRICT=1 — the reference writes whatever inflate produced and says nothing (decompression.cpp:31).
     void report_bad_records(const Archive &a, size_t first_file, const std::vector<uint32_t> &rfile, const std::vector<uint32_t> &status,
-                            Console &con, RunStats &st) {
-        size_t k = 0;
+                            size_t first_rec, Console &con, RunStats &st) {
+        size_t k = first_rec;
         uint32_t cur = 0xffffffffu;
         for (size_t i = 0; i < status.size(); ++i) {
             if (rfile[i] != cur) {
                 cur = rfile[i];
-                k = 0;
+                k = first_rec;
             }
             if (status[i] != ZWZ_STREAM_END) {
                 st.bad_records++;
@@ -271,19 +421,21 @@ class Worker {
         }
     }
 
-    // inflate `nrec` records (payloads already compacted in in_) into out_, retrying with larger capacities for foreign
-    // records that inflate to more than 65 535 bytes (the reference's loop handles any size, decompression.cpp:17-33)
-    void inflate_group(std::vector<uint64_t> &off, std::vector<uint32_t> &len, std::vector<uint32_t> &rfile, uint32_t nf,
-                       std::vector<uint64_t> &foff, uint8_t *digest, std::vector<uint32_t> &status) {
+    // inflate the staged records into out_, retrying with larger capacities for foreign records that inflate to more than
+    // 65 535 bytes (the reference's loop handles any size, decompression.cpp:17-33). digest != NULL: deferred (ticket)
+    void inflate_group(std::vector<uint64_t> &off, std::vector<uint32_t> &len, std::vector<uint32_t> &rfile, uint32_t nf, std::vector<uint64_t> &foff,
+                       uint8_t *digest, uint64_t *ticket, std::vector<uint32_t> &status) {
         const size_t nrec = off.size();
         std::vector<uint32_t> cap(nrec, (uint32_t) CHUNK_SIZE), raw_len(nrec);
         status.assign(nrec, 0u);
         for (int attempt = 0;; ++attempt) {
             uint64_t need = 0;
             for (size_t i = 0; i < nrec; ++i) need += cap[i];
-            out_.reserve(need + 64);
-            int rc = zwz_decompress_records(ctx_, in_.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf, out_.data(),
-                                            out_.cap, foff.data(), raw_len.data(), status.data(), digest, 0);
+            out_.reserve(std::max<size_t>(need, job_.max_out) + 64);
+            int rc = digest ? zwz_decompress_records_async(ctx_, in_.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf,
+                                                           out_.data(), out_.cap, foff.data(), raw_len.data(), status.data(), digest, 0, ticket)
+                            : zwz_decompress_records(ctx_, in_.data(), off.data(), len.data(), cap.data(), rfile.data(), (uint32_t) nrec, nf, out_.data(),
+                                                     out_.cap, foff.data(), raw_len.data(), status.data(), nullptr, 0);
             if (rc != ZWZ_OK) throw std::runtime_error(std::string("zwz_decompress_records: ") + zwz_last_error(ctx_));
             bool again = false;
             for (size_t i = 0; i < nrec; ++i)
@@ -295,120 +447,162 @@ class Worker {
         }
     }
 
-    // copies the payloads of records [r0, r1) of `recs` into in_ back to back, appending their offsets/lengths
-    void stage_payloads(const Span &arch, const std::vector<Rec> &recs, size_t r0, size_t r1, uint64_t &used, std::vector<uint64_t> &off,
-                        std::vector<uint32_t> &len) {
-        for (size_t r = r0; r < r1; ++r) {
-            std::memcpy(in_.data() + used, arch.data() + recs[r].off, recs[r].len);
-            off.push_back(used);
-            len.push_back(recs[r].len);
-            used += recs[r].len;
-        }
+    // copies the payloads of `n` records (described by src[k] = archive offset, len[k]) into in_ back to back
+    void stage_payloads(const Span &arch, const std::vector<uint64_t> &src, const std::vector<uint64_t> &dst, const std::vector<uint32_t> &len) {
+        parallel_for(src.size(), io_threads(), [&](size_t k) { std::memcpy(in_.data() + dst[k], arch.data() + src[k], len[k]); });
     }
 
-    void small_files(const Group &grp, Console &con, RunStats &st) {
+    void small_files(const Group &grp, Pending &p) {
         Archive &a = job_.archives[grp.archive];
+        RunStats &st = p.st;
         const uint32_t nf = (uint32_t) grp.count;
         double t0 = now_seconds();
-        uint64_t comp_bytes = 0;
-        for (size_t f = grp.first; f < grp.first + grp.count; ++f)
-            for (const auto &r : a.files[f].ordered) comp_bytes += r.len;
-        in_.reserve(std::max<size_t>(comp_bytes, job_.max_comp) + 64);
-        out_.reserve(job_.max_out + 64);
-        std::vector<uint64_t> off, foff(nf + 1);
+        std::vector<uint64_t> src, off, foff(nf + 1);
         std::vector<uint32_t> len, rfile;
+        src.reserve(grp.nrec);
         off.reserve(grp.nrec);
         len.reserve(grp.nrec);
         rfile.reserve(grp.nrec);
         uint64_t used = 0;
-        for (size_t f = grp.first; f < grp.first + grp.count; ++f) {
-            stage_payloads(a.bytes, a.files[f].ordered, 0, a.files[f].ordered.size(), used, off, len);
-            rfile.insert(rfile.end(), a.files[f].ordered.size(), (uint32_t) (f - grp.first));
-        }
+        for (size_t f = grp.first; f < grp.first + grp.count; ++f)
+            for (const auto &r : a.files[f].ordered) {
+                src.push_back(r.off);
+                off.push_back(used);
+                len.push_back(r.len);
+                rfile.push_back((uint32_t) (f - grp.first));
+                used += r.len;
+            }
+        in_.reserve(std::max<size_t>(used, job_.max_comp) + 64);
+        stage_payloads(a.bytes, src, off, len);
         st.t_read += now_seconds() - t0;
-        std::vector<uint8_t> digest((size_t) nf * 16);
+        p.digest.assign((size_t) nf * 16, 0);
         t0 = now_seconds();
         std::vector<uint32_t> status;
         if (!off.empty()) {
-            inflate_group(off, len, rfile, nf, foff, digest.data(), status);
-            report_bad_records(a, grp.first, rfile, status, con, st);
+            inflate_group(off, len, rfile, nf, foff, p.digest.data(), &p.ticket, status);
+            report_bad_records(a, grp.first, rfile, status, 0, p.con, st);
+        } else if (nf) { // files without a single usable record: still created, and their verdict is that of the empty file
+            zwz_md5_batch(ctx_, in_.data(), foff.data(), foff.data(), nf, p.digest.data());
         }
-        else if (nf) // files without a single usable record: still created, and their verdict is that of the empty file
-            zwz_md5_batch(ctx_, in_.data(), foff.data(), foff.data(), nf, digest.data());
         st.t_gpu += now_seconds() - t0;
+        // ---- write: directories first (serial, one check per directory), then the files on several threads
         t0 = now_seconds();
-        const RunConfig &cfg = config();
-        for (size_t f = grp.first; f < grp.first + grp.count; ++f) {
-            FileState &fsx = a.files[f];
-            std::string file_path = job_.output_dir + "/" + fsx.relpath;
-            ensure_parent(file_path, last_dir_);
-            std::FILE *o = std::fopen(file_path.c_str(), "wb");
-            if (!o) {
-                con.err << "Error creating output file: " << file_path << "\n";
+        for (size_t f = grp.first; f < grp.first + grp.count; ++f) ensure_parent(job_.output_dir + "/" + a.files[f].relpath, last_dir_);
+        p.files.assign(nf, OutFile{nullptr, 0, false});
+        parallel_for(nf, io_threads(), [&](size_t i) {
+            FileState &fsx = a.files[grp.first + i];
+            const std::string file_path = job_.output_dir + "/" + fsx.relpath;
+            const uint64_t a0 = foff[i], a1 = foff[i + 1];
+            p.files[i].fsx = &fsx;
+            p.files[i].bytes = a1 - a0;
+            int fd = ::open(file_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (fd < 0) return;
+            try {
+                if (a1 > a0) write_all_at(fd, out_.data() + a0, (size_t) (a1 - a0), 0);
+                p.files[i].created = true;
+            } catch (...) {
+            }
+            ::close(fd);
+        });
+        for (uint32_t i = 0; i < nf; ++i) {
+            if (!p.files[i].created) {
+                p.con.err << "Error creating output file: " << job_.output_dir << "/" << p.files[i].fsx->relpath << "\n";
                 continue;
             }
-            uint64_t a0 = foff[f - grp.first], a1 = foff[f - grp.first + 1];
-            if (a1 > a0) std::fwrite(out_.data() + a0, 1, (size_t) (a1 - a0), o);
-            std::fclose(o);
             st.files++;
-            st.records += fsx.ordered.size();
-            st.raw_bytes += a1 - a0;
-            if (fsx.recs.size() != fsx.ordered.size()) con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
-            if (cfg.verbose && !fsx.stored_md5.empty()) con.out << "Read MD5: " << fsx.stored_md5 << "\n"; // decompression.cpp:90
-            if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all)) {
-                char hex[32];
-                zwz_md5_hex(&digest[(f - grp.first) * 16], hex);
-                print_verdict(con, st, file_path, fsx.stored_md5, std::string(hex, 32));
-            }
+            st.records += p.files[i].fsx->ordered.size();
+            st.raw_bytes += p.files[i].bytes;
         }
         st.t_write += now_seconds() - t0;
+        p.active = true;
     }
 
-    // A file whose records do not fit one batch: sub-batches of consecutive records are appended to the output file and the
-    // MD5 is taken the way the reference takes it — by reading the finished file back (decompression.cpp:136).
-    void big_file(Archive &a, FileState &fsx, Console &con, RunStats &st) {
-        const RunConfig &cfg = config();
-        std::string file_path = job_.output_dir + "/" + fsx.relpath;
-        ensure_parent(file_path, last_dir_);
-        std::FILE *o = std::fopen(file_path.c_str(), "wb");
-        if (!o) {
-            con.err << "Error creating output file: " << file_path << "\n";
-            return;
+    // One segment of a file that does not fit a batch: inflate (no digest), learn the offset from the ledger, write. Whoever
+    // writes the last missing segment hashes the finished file the way the reference does — by reading it back
+    // (decompression.cpp:136) — streamed through the GPU.
+    void segment(const Group &grp, Pending &p) {
+        Archive &a = job_.archives[grp.archive];
+        FileState &fsx = a.files[grp.first];
+        BigOut &big = *job_.bigs[(size_t) grp.big];
+        RunStats &st = p.st;
+        double t0 = now_seconds();
+        std::vector<uint64_t> src, off, foff(2);
+        std::vector<uint32_t> len, rfile(grp.r1 - grp.r0, 0u);
+        uint64_t used = 0;
+        for (size_t r = grp.r0; r < grp.r1; ++r) {
+            src.push_back(fsx.ordered[r].off);
+            off.push_back(used);
+            len.push_back(fsx.ordered[r].len);
+            used += fsx.ordered[r].len;
         }
-        const size_t per = std::max<size_t>(1, job_.budget / CHUNK_SIZE);
-        uint64_t written = 0;
-        for (size_t r0 = 0; r0 < fsx.ordered.size(); r0 += per) {
-            size_t r1 = std::min(fsx.ordered.size(), r0 + per);
-            uint64_t comp_bytes = 0;
-            for (size_t r = r0; r < r1; ++r) comp_bytes += fsx.ordered[r].len;
-            in_.reserve(comp_bytes + 64);
-            std::vector<uint64_t> off, foff(2);
-            std::vector<uint32_t> len, rfile(r1 - r0, 0u);
-            uint64_t used = 0;
-            stage_payloads(a.bytes, fsx.ordered, r0, r1, used, off, len);
-            std::vector<uint32_t> status;
-            inflate_group(off, len, rfile, 1, foff, nullptr, status);
-            for (size_t i = 0; i < status.size(); ++i)
-                if (status[i] != ZWZ_STREAM_END) {
-                    st.bad_records++;
-                    if (config().strict) con.err << "Corrupt record: " << fsx.relpath << " sequence " << fsx.ordered[r0 + i].seq << " (" << status_name(status[i]) << ")\n";
-                }
-            if (foff[1]) std::fwrite(out_.data(), 1, (size_t) foff[1], o);
-            written += foff[1];
+        in_.reserve(std::max<size_t>(used, job_.max_comp) + 64);
+        stage_payloads(a.bytes, src, off, len);
+        st.t_read += now_seconds() - t0;
+        t0 = now_seconds();
+        std::vector<uint32_t> status;
+        inflate_group(off, len, rfile, 1, foff, nullptr, nullptr, status);
+        report_bad_records(a, grp.first, rfile, status, grp.r0, p.con, st);
+        st.t_gpu += now_seconds() - t0;
+        const uint64_t bytes = foff[1];
+        // ---- the segment's place in the file
+        t0 = now_seconds();
+        uint64_t at = 0;
+        if (job_.world > 1) {
+            ledger_publish(job_.output_dir, big.key, grp.seg, ".size", bytes);
+            for (int s = 0; s < grp.seg; ++s) at += ledger_wait(job_.output_dir, big.key, s, ".size");
+        } else {
+            std::unique_lock<std::mutex> lock(big.mu);
+            big.cv.wait(lock, [&] { return big.next_seg == grp.seg; });
+            at = big.next_off;
+            big.next_off += bytes;
+            big.next_seg = grp.seg + 1;
+            lock.unlock();
+            big.cv.notify_all();
         }
-        std::fclose(o);
-        st.files++;
-        st.records += fsx.ordered.size();
-        st.raw_bytes += written;
-        if (fsx.recs.size() != fsx.ordered.size()) con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
-        if (fsx.complete && (fsx.verdict_in_order || cfg.verify_all))
-            print_verdict(con, st, file_path, fsx.stored_md5, md5_of_file_ctx(ctx_, file_path));
+        int fd = ::open(big.path.c_str(), O_WRONLY | O_CREAT, 0666);
+        bool ok = fd >= 0;
+        if (ok) {
+            if (bytes) write_all_at(fd, out_.data(), (size_t) bytes, at);
+        } else if (grp.seg == 0) {
+            p.con.err << "Error creating output file: " << big.path << "\n";
+        }
+        st.records += grp.r1 - grp.r0;
+        st.raw_bytes += bytes;
+        st.t_write += now_seconds() - t0;
+        // ---- the last segment to land finishes the file
+        bool finisher;
+        if (job_.world > 1) {
+            ledger_publish(job_.output_dir, big.key, grp.seg, ".done", bytes);
+            finisher = grp.seg == big.nseg - 1;
+            if (finisher)
+                for (int s = 0; s < big.nseg; ++s) ledger_wait(job_.output_dir, big.key, s, ".done");
+        } else {
+            finisher = big.written.fetch_add(1) + 1 == big.nseg;
+        }
+        if (finisher && ok) {
+            const uint64_t total = job_.world > 1 ? at + bytes : big.next_off;
+            if (ftruncate(fd, (off_t) total) != 0) p.con.err << "Error truncating output file: " << big.path << "\n"; // an older, longer file of that name
+        }
+        if (fd >= 0) ::close(fd);
+        if (finisher) {
+            st.files++;
+            if (fsx.recs.size() != fsx.ordered.size()) p.con.err << "Warning: pending chunks remaining for file: " << fsx.relpath << "\n";
+            if (config().verbose && !fsx.stored_md5.empty()) p.con.out << "Read MD5: " << fsx.stored_md5 << "\n";
+            if (ok && fsx.complete && (fsx.verdict_in_order || config().verify_all)) {
+                t0 = now_seconds();
+                print_verdict(p.con, st, job_.output_dir, fsx.relpath, fsx.stored_md5, md5_of_file_ctx(ctx_, big.path));
+                st.t_gpu += now_seconds() - t0;
+            }
+        }
+        p.active = true; // nothing deferred, but the console text goes out through the same door
     }
 
     Job &job_;
     zwz_ctx *ctx_;
     PinnedBuf in_, out_;
     std::string last_dir_;
+    Pending pend_[2];
+    unsigned turn_ = 0;
 };
 
 bool map_archive(Archive &a) {
@@ -435,8 +629,9 @@ bool map_archive(Archive &a) {
 
 } // namespace
 
-// process.hpp:40. The reference runs one thread per archive (decompression.cpp:174); here the groups of all archives feed
-// one worker pool.
+// process.hpp:40. The reference runs one thread per archive (decompression.cpp:174) on rank 0 only (main.cpp:61-69); here the
+// groups of all archives feed one worker pool per rank, and with several ranks (ZWZ_GPUS=N or an external launcher) the
+// groups — whole small files, or record ranges of a large one — are dealt round-robin over the ranks' GPUs.
 void do_decompression(const std::string &input_dir, const std::string &output_dir) {
     const RunConfig &cfg = config();
     std::vector<std::string> names;
@@ -456,27 +651,61 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
         }
     });
     double t0 = now_seconds();
-    std::vector<Archive> archives;
-    archives.reserve(names.size());
-    for (const auto &n : names) {
-        Archive a;
-        a.filename = n;
-        if (!map_archive(a)) {
-            std::cerr << "Error opening file: " << n << std::endl;
-            continue;
+    std::vector<Archive> archives(names.size());
+    std::vector<char> opened(names.size(), 0);
+    parallel_for(names.size(), io_threads() * 2, [&](size_t i) { // archives are independent: index them side by side
+        archives[i].filename = names[i];
+        if (!map_archive(archives[i])) return;
+        opened[i] = 1;
+        parse_archive(archives[i].bytes, archives[i].files);
+    });
+    {
+        std::vector<Archive> kept;
+        for (size_t i = 0; i < archives.size(); ++i) {
+            if (!opened[i]) {
+                std::cerr << "Error opening file: " << names[i] << std::endl;
+                continue;
+            }
+            kept.push_back(std::move(archives[i]));
         }
-        parse_archive(a.bytes, a.files);
-        archives.push_back(std::move(a));
+        archives.swap(kept);
     }
-    // groups of whole files, bounded by the raw bytes they may produce
-    const uint64_t budget = std::max<uint64_t>(cfg.batch_bytes, 4 * CHUNK_SIZE);
+    // groups of whole files, bounded by the raw bytes they may produce; batches small enough that every worker (of every rank)
+    // gets several
+    uint64_t total_rec = 0;
+    for (const auto &a : archives)
+        for (const auto &f : a.files) total_rec += f.ordered.size();
+    const int pool = worker_count();
+    const uint64_t even = total_rec * CHUNK_SIZE / ((uint64_t) pool * 3 * (uint64_t) std::max(1, cfg.world_size)) + 1;
+    const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>(cfg.batch_bytes, std::max<uint64_t>(even, (uint64_t) 8 << 20)), 4 * CHUNK_SIZE);
+    const size_t per_seg = (size_t) std::max<uint64_t>(1, budget / CHUNK_SIZE);
     std::vector<Group> groups;
+    std::vector<std::unique_ptr<BigOut>> bigs;
     for (size_t ai = 0; ai < archives.size(); ++ai) {
         const auto &files = archives[ai].files;
         size_t fi = 0;
         while (fi < files.size()) {
             if (files[fi].ordered.size() * CHUNK_SIZE > budget) {
-                groups.push_back({ai, fi, 1, files[fi].ordered.size(), true});
+                auto big = std::make_unique<BigOut>();
+                big->archive = ai;
+                big->file = fi;
+                big->path = output_dir + "/" + files[fi].relpath;
+                big->key = "a" + std::to_string(ai) + "f" + std::to_string(fi);
+                const size_t nrec = files[fi].ordered.size();
+                for (size_t r0 = 0; r0 < nrec; r0 += per_seg) {
+                    Group g;
+                    g.archive = ai;
+                    g.first = fi;
+                    g.count = 1;
+                    g.segment = true;
+                    g.r0 = r0;
+                    g.r1 = std::min(nrec, r0 + per_seg);
+                    g.nrec = g.r1 - g.r0;
+                    g.big = (int) bigs.size();
+                    g.seg = big->nseg++;
+                    groups.push_back(g);
+                }
+                bigs.push_back(std::move(big));
                 ++fi;
                 continue;
             }
@@ -488,18 +717,33 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
                 nrec += files[fj].ordered.size();
                 ++fj;
             }
-            groups.push_back({ai, fi, fj - fi, nrec, false});
+            Group g;
+            g.archive = ai;
+            g.first = fi;
+            g.count = fj - fi;
+            g.nrec = nrec;
+            groups.push_back(g);
             fi = fj;
         }
     }
     stats().t_read += now_seconds() - t0;
+    if (!bigs.empty()) {
+        std::string last;
+        for (auto &b : bigs) ensure_parent(b->path, last);
+        if (cfg.world_size > 1) {
+            std::error_code ec;
+            fs::create_directories(ledger_dir(output_dir), ec);
+        }
+    }
     warm.join();
     if (warm_error) std::rethrow_exception(warm_error);
 
-    Job job(archives, groups, output_dir, budget, cfg.device);
-    const int workers = (int) std::min<size_t>((size_t) worker_count(), std::max<size_t>(1, groups.size()));
-    if (!groups.empty())
-        run_workers(workers, job.order, [&](int w) {
+    Job job(archives, groups, bigs, output_dir, budget, cfg.device, cfg.world_rank, cfg.world_size);
+    size_t mine = 0;
+    for (size_t g = 0; g < groups.size(); ++g) mine += job.mine(g);
+    const int workers = (int) std::min<size_t>((size_t) pool, std::max<size_t>(1, mine));
+    if (mine)
+        run_workers(workers, job.abort_only, [&](int w) {
             Worker worker(job, w);
             worker.run();
         });

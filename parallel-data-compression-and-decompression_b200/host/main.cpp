@@ -6,14 +6,24 @@
 // `ZWZ_GPUS=8 main compress src dst` shards one directory over the 8 GPUs of a box. Every rank computes the same
 // size-descending deal on its own (same walk, same comparator, same libstdc++ sort), so no broadcast is needed; rank 0
 // also writes <src>/../sorted_files_by_size.txt like the reference does.
+//
+// Where the reference broadcasts the record path and passes a barrier (main.cpp:27-41), the ranks here meet at a marker file
+// in the output directory that is keyed to the RUN: it carries a run id — a nonce the forking parent made (ZWZ_GPUS), or
+// ZWZ_RUN_ID from an external launcher — and a rank only accepts a marker with its own run id (without any id: one no older
+// than two minutes). A marker left by a killed run is therefore never trusted, rank 0 never has to remove it behind the
+// others' backs, and a rank that does not see it within ten minutes fails with a non-zero exit code.
 #include "zwz_host.hpp"
 
 #include <chrono>
 #include <cstdlib>
+#include <algorithm>
+#include <cerrno>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <iostream>
 #include <sys/stat.h>
+#include <thread>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -25,18 +35,48 @@ static void remove_trailing_slash(std::string &path) { // main.cpp:72-76
     if (!path.empty() && path.back() == '/') path.pop_back();
 }
 
-// every rank waits here until rank 0 has published the record file for THIS run (the reference uses MPI_Bcast + MPI_Barrier)
-static bool wait_for_file(const std::string &path, double not_before, double timeout_s) {
+static std::string g_run_id; // ZWZ_RUN_ID, or the nonce of the self-launch
+
+static const char *kReadyMarker = "/.zwz_record_ready";
+
+// marker: "<run id>\n<record file>\n"
+static void publish_marker(const std::string &output_path, const std::string &file_record) {
+    const std::string tmp = output_path + kReadyMarker + ".tmp";
+    {
+        std::ofstream f(tmp);
+        f << g_run_id << "\n" << file_record << "\n";
+    }
+    std::rename(tmp.c_str(), (output_path + kReadyMarker).c_str()); // atomically: a reader sees all of it or none
+}
+
+// every rank but 0 waits here until rank 0 has published the record file for THIS run (the reference uses MPI_Bcast + MPI_Barrier)
+static bool wait_for_marker(const std::string &output_path, double started, double timeout_s, std::string &file_record) {
+    const std::string path = output_path + kReadyMarker;
     double t0 = now_s();
     while (now_s() - t0 < timeout_s) {
-        struct stat st {};
-        if (stat(path.c_str(), &st) == 0 && (double) st.st_mtime + 1.0 >= not_before) return true;
+        std::ifstream f(path);
+        std::string id, rec;
+        if (f.is_open() && std::getline(f, id) && std::getline(f, rec)) {
+            bool ours;
+            if (!g_run_id.empty()) {
+                ours = id == g_run_id;
+            } else { // no run id to compare: accept a marker written around the time this rank started
+                struct stat st {};
+                ours = id.empty() && stat(path.c_str(), &st) == 0 && (double) st.st_mtime >= started - 120.0;
+            }
+            if (ours) {
+                file_record = rec;
+                // tell rank 0 that this rank has the record: it removes the marker once every rank has said so
+                std::ofstream(output_path + kReadyMarker + ".ack" + std::to_string(config().world_rank)) << g_run_id << "\n";
+                return true;
+            }
+        }
         usleep(2000);
     }
     return false;
 }
 
-static void compress(const std::string &folder_path, const std::string &output_path) { // main.cpp:10-54
+static int compress(const std::string &folder_path, const std::string &output_path, double started) { // main.cpp:10-54
     const RunConfig &cfg = config();
     std::string file_record = (std::filesystem::path(folder_path).parent_path() / "sorted_files_by_size.txt").string();
     if (cfg.world_rank == 0) {
@@ -44,12 +84,12 @@ static void compress(const std::string &folder_path, const std::string &output_p
         std::string tmp_record = sort_files_by_size(folder_path);
         std::cout << "File record saved location: " << tmp_record << std::endl;
         file_record = tmp_record;
-        std::ofstream(output_path + "/.zwz_record_ready") << file_record << "\n";
+        if (cfg.world_size > 1) publish_marker(output_path, file_record);
     } else {
-        // the marker lives in the (fresh) output directory, so a stale record file from an earlier run is never trusted
-        if (!wait_for_file(output_path + "/.zwz_record_ready", 0.0, 600.0)) {
-            std::cerr << "Rank: " << cfg.world_rank << " - timed out waiting for the file record" << std::endl;
-            return;
+        const char *to = std::getenv("ZWZ_RENDEZVOUS_TIMEOUT");
+        if (!wait_for_marker(output_path, started, (to && *to) ? std::atof(to) : 600.0, file_record)) {
+            std::cerr << "Rank: " << cfg.world_rank << " - timed out waiting for the file record of this run" << std::endl;
+            return 5;
         }
     }
     std::cout << "file_record: " << file_record << std::endl;
@@ -61,22 +101,36 @@ static void compress(const std::string &folder_path, const std::string &output_p
         std::cout << "Rank: " << cfg.world_rank << " - No file to compress" << std::endl;
     }
     std::cout << "main - Rank: " << cfg.world_rank << " - do_compression finished" << std::endl;
+    if (cfg.world_rank == 0 && cfg.world_size > 1) {
+        // every other rank acknowledges the marker when it has read it; only then may it go (a rank that is still looking for it
+        // would otherwise wait for nothing). A rank that never shows up is a failed job: say so.
+        const char *to = std::getenv("ZWZ_RENDEZVOUS_TIMEOUT");
+        const double limit = (to && *to) ? std::atof(to) : 600.0, t0 = now_s();
+        int missing = cfg.world_size - 1;
+        while (missing > 0 && now_s() - t0 < limit) {
+            missing = 0;
+            for (int r = 1; r < cfg.world_size; ++r) {
+                std::ifstream f(output_path + kReadyMarker + ".ack" + std::to_string(r));
+                std::string id;
+                if (!(f.is_open() && std::getline(f, id) && id == g_run_id)) ++missing;
+            }
+            if (missing) usleep(2000);
+        }
+        if (missing) {
+            std::cerr << "Rank: 0 - " << missing << " rank(s) never picked up the file record of this run" << std::endl;
+            return 5;
+        }
+        std::remove((output_path + kReadyMarker).c_str());
+        for (int r = 1; r < cfg.world_size; ++r) std::remove((output_path + kReadyMarker + ".ack" + std::to_string(r)).c_str());
+    }
+    return 0;
 }
 
-static void decompress(const std::string &source_path, const std::string &output_path) { // main.cpp:56-70
-    const RunConfig &cfg = config();
-    if (cfg.world_rank == 0) {
-        if (cfg.world_size > 1) {
-            std::cout << "Decompression is not supported in MPI parallel mode.\n";
-            std::cout << "Only use one process to decompress.\n";
-        }
-        do_decompression(source_path, output_path);
-    }
-}
+// main.cpp:56-70 leaves decompression to rank 0 ("not supported in MPI parallel mode"). Here every rank takes its share of the
+// batches (decompress_pipeline.cpp): `ZWZ_GPUS=8 main decompress <dir> <out>` uses the 8 GPUs of the box.
+static void decompress(const std::string &source_path, const std::string &output_path) { do_decompression(source_path, output_path); }
 
 namespace {
-
-const char *kReadyMarker = "/.zwz_record_ready";
 
 // rank 0 only (main.cpp:104-129): the source must exist; the output directory is created when missing
 bool prepare_paths(const std::string &source_path, const std::string &output_path) {
@@ -87,7 +141,7 @@ bool prepare_paths(const std::string &source_path, const std::string &output_pat
         return false;
     }
     if (!fs::exists(output_path, ec)) {
-        if (mkdir(output_path.c_str(), 0777) == -1) {
+        if (mkdir(output_path.c_str(), 0777) == -1 && errno != EEXIST) { // EEXIST: another rank of this run was faster
             perror("Failed to create output directory");
             return false;
         }
@@ -147,20 +201,37 @@ int main(int argc, char *argv[]) {
     std::cout << "output_path: " << output_path << '\n';
 
     const bool compressing = operation == "compress";
+    const bool decompressing = operation == "decompress";
+    if (const char *id = std::getenv("ZWZ_RUN_ID")) g_run_id = id;
     if (cfg.world_rank == 0) {
         if (!prepare_paths(source_path, output_path)) return 1;
-        if (compressing) std::remove((output_path + kReadyMarker).c_str());
+        if (compressing) { // whatever an earlier run left
+            std::remove((output_path + kReadyMarker).c_str());
+            for (int r = 1; r < std::max(cfg.world_size, 64); ++r) std::remove((output_path + kReadyMarker + ".ack" + std::to_string(r)).c_str());
+        }
+        if (decompressing) {
+            std::error_code ec;
+            std::filesystem::remove_all(output_path + "/.zwz_segments", ec);
+        }
     }
     const char *g = std::getenv("ZWZ_GPUS");
     const int self_gpus = (g && cfg.world_size == 1) ? std::atoi(g) : 0;
     std::vector<pid_t> kids;
-    if (self_gpus > 1 && compressing) kids = fork_ranks(self_gpus);
+    if (self_gpus > 1 && (compressing || decompressing)) {
+        if (g_run_id.empty()) g_run_id = "self-" + std::to_string((long) getpid()) + "-" + std::to_string((long long) (start_time * 1e6));
+        kids = fork_ranks(self_gpus);
+    }
+
+    // the CUDA runtime and this rank's first context come up (0.6–2.5 s on a fresh box) while the host walks and sorts the tree
+    // or maps and indexes the archives
+    std::thread warm;
+    if (compressing || decompressing) warm = std::thread([] { zwzhost::warm_device(); });
 
     int rc = 0;
     try {
         if (compressing) {
-            compress(source_path, output_path);
-        } else if (operation == "decompress") {
+            rc = compress(source_path, output_path, (double) std::time(nullptr));
+        } else if (decompressing) {
             decompress(source_path, output_path);
         } else {
             std::cerr << "Invalid operation: " << operation << ". Please use 'compress' or 'decompress'.\n";
@@ -170,19 +241,27 @@ int main(int argc, char *argv[]) {
         std::cerr << "Rank: " << cfg.world_rank << " - fatal: " << e.what() << std::endl;
         rc = 2;
     }
+    if (warm.joinable()) warm.join();
     timing_mark("operation finished");
     if (cfg.strict && stats().bad_records != 0 && rc == 0) {
         std::cerr << "ZWZ_STRICT: " << stats().bad_records << " record(s) did not decode cleanly" << std::endl;
         rc = 4;
     }
-    if (self_gpus > 1 && compressing && cfg.world_rank != 0) _exit(rc); // a forked rank: no summary, no waiting
+    if (self_gpus > 1 && cfg.world_rank != 0) { // a forked rank: no summary, no waiting
+        std::cout << std::flush;
+        std::cerr << std::flush;
+        _exit(rc);
+    }
     for (pid_t k : kids) {
         int st = 0;
         waitpid(k, &st, 0);
         if ((!WIFEXITED(st) || WEXITSTATUS(st) != 0) && rc == 0) rc = 3;
     }
     if (cfg.world_rank == 0) {
-        if (compressing) std::remove((output_path + kReadyMarker).c_str());
+        if (!kids.empty()) { // every rank of a self-launched run has finished: the run's scratch files can go
+            std::error_code ec;
+            std::filesystem::remove_all(output_path + "/.zwz_segments", ec);
+        }
         print_summary(operation, now_s() - start_time);
     }
     return rc;

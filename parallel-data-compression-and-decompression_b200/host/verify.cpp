@@ -34,6 +34,13 @@ zwz_ctx *ctx_for(int device) {
     return c;
 }
 
+void warm_device() {
+    try {
+        ctx_for(config().device);
+    } catch (...) {
+    }
+}
+
 // the extra contexts of the worker pool (pipeline.hpp): cheap once the device's primary context exists
 zwz_ctx *worker_ctx(int device, int worker) {
     if (worker <= 0) return ctx_for(device);
@@ -62,8 +69,8 @@ int worker_count() {
         // rank may use (the ranks of one box share them), at least 3
         int cores = (int) std::thread::hardware_concurrency();
         int local_ranks = std::max(1, std::min(config().world_size, std::max(1, visible_gpu_count())));
-        w = std::max(3, cores / local_ranks / 2);
-        w = std::min(w, 8);
+        w = std::max(3, cores / local_ranks / 4);
+        w = std::min(w, 6);
     }
     return w < 1 ? 1 : (w > 12 ? 12 : w);
 }

@@ -39,11 +39,14 @@ struct RunConfig {
     bool verify_all = false;  // also print an MD5 verdict for files whose last record arrived out of order
     bool strict = false;      // ZWZ_STRICT=1: name every record that did not decode to a clean end of stream, exit code 4
                               // (the reference ignores zlib's return codes, decompression.cpp:31 — and so does the default)
+    bool quarantine = false;  // ZWZ_QUARANTINE=1: move files whose MD5 does not match to <output dir>/bad/ (README.md:175,186 promises
+                              // it; the reference's code leaves them in place, and so does the default)
     std::size_t batch_bytes = (std::size_t) 128 << 20; // per worker (ZWZ_BATCH_MB)
 };
 RunConfig &config();
 void config_from_env();
 int visible_gpu_count(); // without initialising CUDA when possible
+void warm_device();      // bring up this rank's CUDA context (errors are left for the first real use to report)
 
 // deterministic walk + size-descending sort, shared by sort_files_by_size and by ranks that recompute the deal
 std::vector<FileEntry> collect_and_sort(const std::filesystem::path &path);

@@ -224,6 +224,106 @@ def test_self_round_trip_and_multi_batch(main_bin, tmp_path):
     same_tree(str(src), out1)
 
 
+def _small_tree(tmp_path, with_big=True):
+    src = tmp_path / "w" / "src"
+    src.mkdir(parents=True)
+    specs = corpus.c1_specs(10, seed=601, min_size=2000, max_size=200_000)
+    if with_big:
+        specs.append(corpus.FileSpec("big/huge.log", 3_300_000, "T", 998))   # cut into segments with ZWZ_BATCH_MB=1
+    corpus.write_tree(str(src), specs, 601)
+    return str(src), specs
+
+
+def test_stale_marker_of_a_killed_run_is_not_trusted(main_bin, tmp_path):
+    """a `.zwz_record_ready` left by a killed run (plus its old record file) must not let rank 1 deal from the old
+    list when it starts before rank 0. The marker carries the run id; a rank without its run's marker fails after the
+    rendezvous timeout instead of exiting 0."""
+    src, specs = _small_tree(tmp_path, with_big=False)
+    arch = tmp_path / "arch"
+    arch.mkdir()
+    record = os.path.join(os.path.dirname(src), "sorted_files_by_size.txt")
+    open(record, "w").write("\n".join(s.relpath for s in specs[:3]) + "\n")          # what the killed run left: a partial list
+    (arch / ".zwz_record_ready").write_text("killed-run\n" + record + "\n")
+    env = {**os.environ, "ZWZ_WORLD": "2", "ZWZ_RUN_ID": "run-42", "ZWZ_RENDEZVOUS_TIMEOUT": "60"}
+    p1 = subprocess.Popen([main_bin, "compress", src, str(arch)], env={**env, "ZWZ_RANK": "1"}, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    import time
+    time.sleep(1.0)                                                                      # rank 1 is polling; the stale marker is all there is
+    assert p1.poll() is None
+    p0 = subprocess.Popen([main_bin, "compress", src, str(arch)], env={**env, "ZWZ_RANK": "0"}, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    for p in (p0, p1):
+        p.communicate()
+        assert p.returncode == 0
+    got = set()
+    for a in ("compressed_0.zwz", "compressed_1.zwz"):
+        got |= {r.path for r in zwz_format.parse(open(os.path.join(str(arch), a), "rb").read())}
+    assert got == {s.relpath for s in specs}                                             # nothing dealt from the stale list
+    # and alone, with only a foreign marker to look at, a rank gives up with a non-zero exit code
+    r = subprocess.run([main_bin, "compress", src, str(arch)], env={**env, "ZWZ_RANK": "1", "ZWZ_RUN_ID": "run-43", "ZWZ_RENDEZVOUS_TIMEOUT": "1"},
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "timed out" in r.stderr
+
+
+def test_generic_rank_variables_do_not_shard(main_bin, tmp_path):
+    """RANK/WORLD_SIZE of an enclosing torch/k8s job must not turn a plain run into rank r of N."""
+    src, specs = _small_tree(tmp_path, with_big=False)
+    arch = str(tmp_path / "arch")
+    log = run([main_bin, "compress", src, arch], {"RANK": "1", "WORLD_SIZE": "4", "LOCAL_RANK": "1"})
+    assert "Processor Count: 1" in log and os.listdir(arch) == ["compressed_0.zwz"]
+    assert {r.path for r in zwz_format.parse(open(os.path.join(arch, "compressed_0.zwz"), "rb").read())} == {s.relpath for s in specs}
+
+
+def test_verify_all_gives_the_verdict_the_reference_skips(main_bin, tmp_path):
+    """decompression.cpp:132 only judges a file when its is_last record arrives in order; the hand-built foreign archive has a
+    file whose last record comes first. ZWZ_VERIFY_ALL=1 prints a verdict for every complete file."""
+    man = json.load(open(os.path.join(GOLD, "manifest.json")))
+    o1, o2 = str(tmp_path / "o1"), str(tmp_path / "o2")
+    base = run([main_bin, "decompress", os.path.join(GOLD, "foreign"), o1])
+    full = run([main_bin, "decompress", os.path.join(GOLD, "foreign"), o2], {"ZWZ_VERIFY_ALL": "1"})
+    n_files = len(man["foreign"]["outputs"])
+    assert base.count("MD5 match for file") + base.count("MD5 mismatch for file") == man["foreign"]["verdicts"]["match"] + man["foreign"]["verdicts"]["mismatch"] < n_files
+    assert full.count("MD5 match for file") + full.count("MD5 mismatch for file") == n_files
+    same_tree(o1, o2)
+
+
+def test_quarantine_moves_mismatching_files_to_bad(main_bin, tmp_path):
+    """README.md:175,186 promise a bad/ directory for files whose MD5 does not match; the reference's code leaves them in place
+    (and so does the default). ZWZ_QUARANTINE=1 moves them. The golden 1-rank archive holds the reference's own lossy record."""
+    man = json.load(open(os.path.join(GOLD, "manifest.json")))
+    assert man["edge_r1"]["verdicts"]["mismatch"] == 1
+    out = str(tmp_path / "out")
+    log = run([main_bin, "decompress", os.path.join(GOLD, "edge_r1"), out], {"ZWZ_QUARANTINE": "1"})
+    assert log.count("MD5 mismatch for file") == 1 and "Moved to: " in log
+    bad = [os.path.relpath(os.path.join(d, f), os.path.join(out, "bad")) for d, _, fs_ in os.walk(os.path.join(out, "bad")) for f in fs_]
+    assert bad == ["rand70k.bin"] and not os.path.exists(os.path.join(out, "rand70k.bin"))
+    b = open(os.path.join(out, "bad", "rand70k.bin"), "rb").read()
+    assert {"size": len(b), "md5": hashlib.md5(b).hexdigest()} == man["edge_r1"]["outputs"]["rand70k.bin"]
+
+
+@pytest.mark.parametrize("launch", ["ranks", "self"])
+def test_multi_rank_decompress(main_bin, tmp_path, launch):
+    """the reference decompresses on rank 0 only (main.cpp:61-69). Here the batches — whole small files and
+    record ranges of a large one (segments, offsets through the shared ledger) — are dealt over the ranks: two ranks started by
+    a launcher (ZWZ_RANK/ZWZ_WORLD) or forked by `ZWZ_GPUS=2 main decompress`; same tree, one verdict per file."""
+    src, specs = _small_tree(tmp_path)
+    arch, out = str(tmp_path / "arch"), str(tmp_path / "out")
+    run([main_bin, "compress", src, arch], {"ZWZ_GPUS": "2", "ZWZ_BATCH_MB": "1"})
+    if launch == "self":
+        log = run([main_bin, "decompress", arch, out], {"ZWZ_GPUS": "2", "ZWZ_BATCH_MB": "1"})
+        assert "Processor Count: 2" in log
+    else:
+        env = {**os.environ, "ZWZ_WORLD": "2", "ZWZ_BATCH_MB": "1", "ZWZ_RUN_ID": "d1"}
+        procs = [subprocess.Popen([main_bin, "decompress", arch, out], env={**env, "ZWZ_RANK": str(r)}, stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in (0, 1)]
+        log = ""
+        for p in procs:
+            log += p.communicate()[0]
+            assert p.returncode == 0
+    assert log.count("MD5 match for file") == len(specs) and "mismatch" not in log
+    assert not os.path.exists(os.path.join(out, ".zwz_segments")) or launch == "ranks"
+    shutil.rmtree(os.path.join(out, ".zwz_segments"), ignore_errors=True)
+    same_tree(src, out)
+
+
 def test_usage_and_errors(main_bin, tmp_path):
     r = subprocess.run([main_bin, "compress"], capture_output=True, text=True)
     assert r.returncode != 0 and "Usage:" in r.stderr

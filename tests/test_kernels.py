@@ -135,6 +135,63 @@ def test_inflate_truncated_and_corrupted(ctx_inf, is_gpu):
     _check_inflate(ctx_inf, cases, 70000)
 
 
+class _Bits:
+    """LSB-first bit writer; Huffman codes go in MSB-first (RFC 1951 §3.1.1)."""
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, v, nb):
+        self.acc |= v << self.n
+        self.n += nb
+        while self.n >= 8:
+            self.out.append(self.acc & 255)
+            self.acc >>= 8
+            self.n -= 8
+
+    def code(self, v, nb):
+        self.put(int(format(v, f"0{nb}b")[::-1], 2), nb)
+
+    def lit(self, b):   # fixed code, RFC 1951 §3.2.6
+        self.code(0x30 + b, 8) if b < 144 else self.code(0x190 + b - 144, 9)
+
+    def match3(self, dist_sym, extra, ebits):   # length 3 (symbol 257: 0000001) + a distance symbol
+        self.code(1, 7)
+        self.code(dist_sym, 5)
+        self.put(extra, ebits)
+
+    def finish(self):
+        self.code(0, 7)   # end of block
+        if self.n:
+            self.out.append(self.acc & 255)
+        return bytes(self.out)
+
+
+def test_inflate_distance_too_far_back(ctx_inf):
+    """zlib: "invalid distance too far back" — everything before the offending match is written, then the stream is bad.
+    Hand-made fixed-Huffman streams: the bad match first thing, behind literals, behind valid matches, deep inside a long block."""
+    cases = []
+    for nlit, good in [(0, 0), (1, 0), (40, 0), (40, 5), (3000, 40), (9000, 300)]:
+        w = _Bits()
+        w.put(0x9c78, 16)
+        w.put(1, 1)
+        w.put(1, 2)
+        produced = 0
+        for i in range(nlit):
+            w.lit((i * 7 + 3) & 0x7f)
+            produced += 1
+            if good and i % (nlit // good) == 5:
+                w.match3(2, 0, 0)   # distance 3: fine
+                produced += 3
+        # distance symbol 29 + 13 extra bits = 24577 + 8191 = 32768 > produced
+        w.match3(29, 8191, 13)
+        w.lit(65)
+        cases.append(w.finish() + b"\0\0\0\0")
+    for c in cases:
+        want, wst, wn = O.inflate(c, 70000)
+        assert wst == O.STREAM_BAD
+    _check_inflate(ctx_inf, cases, 70000)
+
+
 def test_inflate_output_capacity(ctx_inf):
     raw = corpus.gen_text(9000, 596, 3).tobytes()
     streams = [zlib.compress(raw), zlib.compress(raw[:100]), zlib.compress(b"")]

@@ -259,12 +259,14 @@ def c2_specs(n_files: int = 370_000, seed: int = BASE_SEED) -> List[FileSpec]:
     return [FileSpec(f"dir{i // 1000:03d}/img{i % 1000:04d}.dat", int(sizes[i]), "I", i) for i in range(n_files)]
 
 
-def c2_buffer(n_files: int = 370_000, seed: int = BASE_SEED) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def c2_buffer(n_files: int = 370_000, seed: int = BASE_SEED, sizes=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Whole C2 corpus as ONE contiguous buffer (fast path for bench.py): returns (bytes, offsets[n+1], sizes[n]).
 
-    Keyed per 1 000-file directory: (seed, dir_index). 70 % of files JPEG-like, 30 % raw-bitmap-like.
+    Keyed per 1 000-file directory: (seed, dir_index). 70 % of files JPEG-like, 30 % raw-bitmap-like. `sizes`: generate the
+    files at these sizes (a rank's share of the size-sorted deal) instead of drawing them.
     """
-    sizes = c2_sizes(n_files, seed)
+    sizes = c2_sizes(n_files, seed) if sizes is None else np.asarray(sizes, dtype=np.int64)
+    n_files = len(sizes)
     offs = np.zeros(n_files + 1, dtype=np.int64)
     np.cumsum(sizes, out=offs[1:])
     buf = np.empty(int(offs[-1]), dtype=np.uint8)
