@@ -464,6 +464,7 @@ def main():
     ap.add_argument("--cpu-sample-mb", type=float, default=0.0, help="CPU baseline sample size (default: ~15 s of work)")
     ap.add_argument("--ref-sample-mb", type=float, default=0.0, help="--impl reference: sample size (default: 1 GB at 25 steps, scaled so the run ends in minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg (its line then carries e2e = null)")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C1/C3-shaped device passes of the default c2 line")
     ap.add_argument("--e2e-workers", type=int, default=0, help="end-to-end leg: worker contexts (stream + buffers each) per rank; 0 = min(6, host cores / ranks), at least 2")
     ap.add_argument("--e2e-parts", type=int, default=32, help="end-to-end leg: parts the shard is cut into")
@@ -675,20 +676,24 @@ def main():
     ctx.profile_enable(False)
 
     # e2e
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    wl0 = sum(w.launches for w in workers)
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e3.record()
-    barrier()
-    e2e_ms = e2.elapsed_time(e3)
-    e2e_launches = sum(w.launches for w in workers) - wl0
+    e2e_ms, e2e_launches = float("nan"), 0
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        wl0 = sum(w.launches for w in workers)
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e3.record()
+        barrier()
+        e2e_ms = e2.elapsed_time(e3)
+        e2e_launches = sum(w.launches for w in workers) - wl0
     clocks = sampler.stop()
-    if sh.periodic:   # what every worker wrote last
+    if args.no_e2e:
+        pass
+    elif sh.periodic:   # what every worker wrote last
         for wi, i in enumerate(last_part):
             if i is not None:
                 d = part_desc[i]
@@ -748,8 +753,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / max(nl[dom], 1), "launches": nl[dom]},
-            "e2e": {"value": U_all * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(U + state["C"]),
-                    "d2h_bytes_per_step": int(U + state["C"]), "ms_per_step": e2e_ms / K},
+            "e2e": None if args.no_e2e else {"value": U_all * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(U + state["C"]),
+                                             "d2h_bytes_per_step": int(U + state["C"]), "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }

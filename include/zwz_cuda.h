@@ -166,6 +166,13 @@ int zwz_decompress_records(zwz_ctx *ctx, const uint8_t *comp, const uint64_t *of
                            const uint32_t *rec_file, uint32_t n, uint32_t nf, uint8_t *files_out, uint64_t out_cap, uint64_t *file_off_out,
                            uint32_t *raw_len, uint32_t *status, uint8_t *digest /* nf*16 or NULL */, uint32_t flags);
 
+/* Tuning knobs of a context. ZWZ_TUNE_DEFLATE_SUBBATCH_BYTES: raw bytes deflated per internal pass (default 4 GiB; the
+ * match/token scratch is 6 bytes per raw byte of ONE pass, so a host worker that feeds 128 MB batches asks for 32 MiB passes
+ * and its context allocates 0.2 GB of scratch instead of 0.8 GB — device allocation is the larger part of a short job's
+ * start-up). */
+#define ZWZ_TUNE_DEFLATE_SUBBATCH_BYTES 1
+int zwz_ctx_tune(zwz_ctx *ctx, int what, uint64_t value);
+
 /* ---- asynchronous forms: the digests are DEFERRED ----------------------------------------------------------------------
  * "asynchronous variants ... pair with a zwz_wait". A file's MD5 is one serial chain (~0.13 GB/s per file on
  * one lane), so a batch holding a 16 MiB file would wait ~130 ms for its digests while its deflate/inflate kernels take a

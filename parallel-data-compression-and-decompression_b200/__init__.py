@@ -82,6 +82,10 @@ def _declare(L):
     L.zwz_adler32_batch_device.argtypes = [vp, vp, vp, vp, u32, vp, vp]
     L.zwz_compress_files.argtypes = [vp, vp, vp, u32, i32, vp, u64, vp, vp, vp]
     L.zwz_decompress_records.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, vp, u64, vp, vp, vp, vp, u32]
+    L.zwz_ctx_tune.argtypes = [vp, i32, u64]
+    L.zwz_compress_files_async.argtypes = [vp, vp, vp, u32, i32, vp, u64, vp, vp, vp, vp]
+    L.zwz_decompress_records_async.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, vp, u64, vp, vp, vp, vp, u32, vp]
+    L.zwz_wait.argtypes = [vp, u64]
     L.zwz_profile_enable.argtypes = [vp, i32]
     L.zwz_profile_read.argtypes = [vp, vp, vp, i32]
     return L

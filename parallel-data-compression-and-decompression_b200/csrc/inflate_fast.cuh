@@ -253,8 +253,9 @@ ZWZ_DEV int inf_fast_block(SMEM &S, const BITS &B, uint64_t &bitpos, uint32_t ma
                         if ((hm >> j) & 1u) {
                             const uint32_t i = b - ej;                                                // byte i of the match
                             const uint32_t src = ej + (dj >= (tj & 0x1ffu) || i < dj ? i : i % dj);   // its source + dist, relative to the step
-                            // before the step iff src < dj; a too-far match (dj > pos + ej) is never written out: skip its loads
-                            if (src < dj && dj <= pos + ej) stg[b] = __ldcg(out + (pos + src - dj));
+                            // before the step iff src < dj. No load for bytes that will not be written: those of a too-far match
+                            // (dj > pos + ej) and those past the capacity of the output window (a sizing pass still counts them)
+                            if (src < dj && dj <= pos + ej && pos + b < cap) stg[b] = __ldcg(out + (pos + src - dj));
                         } else {
                             stg[b] = (uint8_t) tj;
                         }

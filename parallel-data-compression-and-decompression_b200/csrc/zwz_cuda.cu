@@ -314,6 +314,16 @@ void zwz_destroy(zwz_ctx *ctx) {
 
 const char *zwz_last_error(const zwz_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
+int zwz_ctx_tune(zwz_ctx *ctx, int what, uint64_t value) {
+    if (!ctx) return ZWZ_E_ARG;
+    if (what == ZWZ_TUNE_DEFLATE_SUBBATCH_BYTES) {
+        if (value < ((uint64_t) 1 << 20)) return fail(ctx, ZWZ_E_ARG, "sub-batch below 1 MiB");
+        ctx->batch_raw_bytes = (size_t) value;
+        return ZWZ_OK;
+    }
+    return fail(ctx, ZWZ_E_ARG, "unknown tuning knob");
+}
+
 int zwz_device_props(const zwz_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
     if (!ctx) return ZWZ_E_ARG;
     if (sm_count) *sm_count = ctx->sm_count;
