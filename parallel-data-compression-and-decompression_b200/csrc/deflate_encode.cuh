@@ -48,10 +48,13 @@ struct EncWarpSmem {
     uint8_t cl_ext[320];
     uint32_t stage[64];     // bit sink staging window
     uint32_t misc[8];
-    uint32_t region[16];    // stored regions of the chunk: token ranges [region[2i], region[2i+1])
+    uint32_t region[16];    // stored regions of the chunk: {first token, end token, first byte, end byte} x 4
     uint32_t tflags[ZWZ_SCR_FLAG_WORDS]; // bit t: the 32-position tile t holds a match (its scratch words are valid)
-    uint16_t kb_tok[66];    // token index / byte position of the first parse step inside every 1 024-byte stretch
-    uint16_t kb_pos[66];
+    uint16_t kb_tok[66];    // token count before the first parse step that STARTS inside each 1 024-byte stretch (tokens from
+                            // there on start inside it or later)
+    uint16_t kb_end[66];    // token count before the first parse step that REACHES into the stretch (tokens before it start earlier)
+    uint16_t kb_pos[66];    // byte positions of those two steps
+    uint16_t kb_endpos[66];
 };
 #define ZWZ_DE_SMEM (ZWZ_DE_WARPS * (uint32_t) sizeof(zwz::EncWarpSmem))
 
@@ -555,34 +558,40 @@ ZWZ_DEV_NOINLINE void enc_emit_block(BitSink *kp, const uint32_t *m, uint32_t t0
 
 #define ZWZ_DE_STORED_MIN 512u // literal tokens in a row before a stored region is considered
 
-// Stored-region candidates come for free from the match kernel's tile flags: a 1 024-byte stretch whose flag word is zero holds
-// no match at all, so the tokens that start in it are literals. Runs of such stretches with at least ZWZ_DE_STORED_MIN tokens
-// whose byte histogram leaves a Huffman code less than n/256 bytes + 8 to gain become S.region[] (token ranges, from the marks
-// the parse left in S.kb_tok). Returns their number (at most 8).
+// Stored-region candidates come for free from the match kernel's tile flags: a 1 024-byte stretch with matches in at most
+// ZWZ_DE_QUIET_TILES of its 32 tiles is (nearly) match-free — uniformly random bytes still repeat a 3-byte string now and then.
+// Runs of such stretches whose tokens leave a Huffman code less than n/256 bytes + 8 to gain over plain bytes become
+// S.region[] = {first token, end token, first byte, end byte} (from the marks the parse left). At most 4 per chunk.
+#define ZWZ_DE_QUIET_TILES 3
 ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t n, uint32_t ntok) {
     EncWarpSmem &S = enc_smem();
     const unsigned lane = lane_id();
     const uint32_t nkb = (n + 1023u) >> 10;
-    const unsigned q0 = __ballot_sync(ZWZ_FULL, lane < nkb && S.tflags[lane] == 0u);
-    const unsigned q1 = __ballot_sync(ZWZ_FULL, lane + 32u < nkb && S.tflags[lane + 32u] == 0u);
+    const unsigned q0 = __ballot_sync(ZWZ_FULL, lane < nkb && __popc(S.tflags[lane]) <= ZWZ_DE_QUIET_TILES);
+    const unsigned q1 = __ballot_sync(ZWZ_FULL, lane + 32u < nkb && __popc(S.tflags[lane + 32u]) <= ZWZ_DE_QUIET_TILES);
     uint64_t quiet = (uint64_t) q0 | ((uint64_t) q1 << 32);
     uint32_t nreg = 0;
-    while (quiet && nreg < 8u) { // warp-uniform
+    while (quiet && nreg < 4u) { // warp-uniform
         const uint32_t a = (uint32_t) __ffsll((long long) quiet) - 1u;
         uint64_t rest = ~(quiet >> a); // first zero above a ends the run
         const uint32_t len = rest ? (uint32_t) __ffsll((long long) rest) - 1u : 64u - a;
         const uint32_t b = a + len;
         quiet = b >= 64u ? 0ull : quiet & ~((1ull << b) - 1ull);
-        const uint32_t r0 = S.kb_tok[a], r1 = b < nkb ? S.kb_tok[b] : ntok;
-        if (r1 > r0 && r1 - r0 >= ZWZ_DE_STORED_MIN) {
-            enc_hist_tokens(m, r0, r1, true); // into S.code: S.freq keeps the whole-chunk histogram
+        // tokens [r0, r1) = bytes [p0, p1): from the first step that starts in stretch a up to the first step that reaches into
+        // stretch b (a step that starts in b - 1 may already emit tokens of b's first positions)
+        const uint32_t r0 = S.kb_tok[a], r1 = b < nkb ? S.kb_end[b] : ntok;
+        const uint32_t p0 = S.kb_pos[a], p1 = b < nkb ? S.kb_endpos[b] : n;
+        if (r1 > r0 && p1 > p0 && p1 - p0 >= ZWZ_DE_STORED_MIN) {
+            const uint64_t xb = enc_hist_tokens(m, r0, r1, true); // into S.code: S.freq keeps the whole-chunk histogram
             uint32_t nu;
-            const float h_bits = enc_entropy_bits(1u, &nu);
-            const float nb = (float) (r1 - r0);
+            const float h_bits = enc_entropy_bits(1u, &nu) + (float) xb;
+            const float nb = (float) (p1 - p0);
             if (8.f * nb - h_bits < nb * (1.f / 32.f) + 64.f) {
                 if (lane == 0) {
-                    S.region[2u * nreg] = r0;
-                    S.region[2u * nreg + 1u] = r1;
+                    S.region[4u * nreg] = r0;
+                    S.region[4u * nreg + 1u] = r1;
+                    S.region[4u * nreg + 2u] = p0;
+                    S.region[4u * nreg + 3u] = p1;
                 }
                 ++nreg;
             }
@@ -592,13 +601,12 @@ ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t n,
     return nreg;
 }
 
-// The literal tokens [t0, t1) as one stored block (RFC 1951 §3.2.4): 3 header bits, pad to a byte boundary, LEN, NLEN, bytes.
-ZWZ_DEV_NOINLINE void enc_emit_stored_block(BitSink *kp, const uint32_t *m, uint32_t t0, uint32_t t1, bool last) {
+// The raw bytes src[0, nbytes) as one stored block (RFC 1951 §3.2.4): 3 header bits, pad to a byte boundary, LEN, NLEN, bytes.
+ZWZ_DEV_NOINLINE void enc_emit_stored_block(BitSink *kp, const uint8_t *src, uint32_t nbytes, bool last) {
     EncWarpSmem &S = enc_smem();
     BitSink k = *kp;
     const unsigned lane = lane_id();
-    const uint32_t nbytes = t1 - t0; // <= 65 535: a chunk has no more bytes
-    const uint32_t at = k.nwords * 32u + k.fill + 3u;
+    const uint32_t at = k.nwords * 32u + k.fill + 3u; // nbytes <= 65 535: a chunk has no more
     const uint32_t pad = (8u - (at & 7u)) & 7u;
     uint64_t v = 0;
     uint32_t nb = 0;
@@ -610,13 +618,13 @@ ZWZ_DEV_NOINLINE void enc_emit_stored_block(BitSink *kp, const uint32_t *m, uint
         nb = 32u;
     }
     sink_put(S, k, v, nb);
-    for (uint32_t base = t0; base < t1; base += 128u) {
+    for (uint32_t base = 0; base < nbytes; base += 128u) {
         const uint32_t i = base + 4u * lane;
         uint32_t w = 0, cnt = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 4u; ++j)
-            if (i + j < t1) {
-                w |= tok_byte(m[i + j]) << (8u * j);
+            if (i + j < nbytes) {
+                w |= (uint32_t) src[i + j] << (8u * j);
                 ++cnt;
             }
         sink_put(S, k, (uint64_t) w, 8u * cnt);
@@ -712,16 +720,24 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     __syncwarp();
 #define ENC_WORD_AT(x_) ((x_) < n ? (((S.tflags[(x_) >> 10] >> (((x_) >> 5) & 31u)) & 1u) ? m[(x_)] : ((uint32_t) src[(x_)] << 24)) : 0u)
     uint32_t ntok = 0;
-    uint32_t last_kb = 0xffffffffu;
+    uint32_t last_kb = 0xffffffffu, last_kbe = 0xffffffffu;
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)
     uint32_t m0 = ENC_WORD_AT(lane);
     for (uint32_t p = 0; p < n;) {
         uint32_t q = p + lane;
-        if ((p >> 10) != last_kb) { // first step inside this 1 024-byte stretch: a token boundary the stored regions can use
+        // token boundaries the stored regions can use: a step looks at positions [p, p + 32)
+        if ((p >> 10) != last_kb) {
             last_kb = p >> 10;
             if (lane == 0) {
                 S.kb_tok[last_kb] = (uint16_t) ntok;
                 S.kb_pos[last_kb] = (uint16_t) p;
+            }
+        }
+        if (((p + 31u) >> 10) != last_kbe) {
+            last_kbe = (p + 31u) >> 10;
+            if (lane == 0) {
+                S.kb_end[last_kbe] = (uint16_t) ntok;
+                S.kb_endpos[last_kbe] = (uint16_t) p;
             }
         }
         // the window after this one, fetched before it is known to be needed: when the window holds no match that leaves
@@ -840,9 +856,9 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     } else {
         uint32_t t = 0;
         for (uint32_t r = 0; r < nreg; ++r) {
-            const uint32_t r0 = S.region[2u * r], r1 = S.region[2u * r + 1u];
+            const uint32_t r0 = S.region[4u * r], r1 = S.region[4u * r + 1u], p0 = S.region[4u * r + 2u], p1 = S.region[4u * r + 3u];
             if (r0 > t) enc_emit_range(&k, m, t, r0, 0, false, false);
-            enc_emit_stored_block(&k, m, r0, r1, r1 == ntok);
+            enc_emit_stored_block(&k, src + p0, p1 - p0, r1 == ntok);
             t = r1;
         }
         if (t < ntok) enc_emit_range(&k, m, t, ntok, 0, true, false);

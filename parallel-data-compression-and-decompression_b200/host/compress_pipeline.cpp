@@ -15,6 +15,14 @@
 //     zwz_wait delivers the digests, then go to the archive with ONE pwrite at the offset reserved earlier;
 //   * a file cut into segments is hashed by a separate hasher thread that streams it through zwz_md5_update_device on its
 //     own context while all workers deflate its segments; only the record that carries the digest waits for it.
+//
+// One file over several GPUs (BASELINE config 3: a single 16 GB file). The reference's deal is file-granular
+// (compression.cpp:31-41), so such a file lands on one rank and one deflate thread, and its reader wants all records of a
+// path in ONE archive (decompression.cpp:52-55). Here the segments of a file that is cut are dealt over the ranks of the run:
+// the file's owner (the rank the deal gives it to) keeps the archive order and hands every segment its place — archive
+// offset and first sequence id — as soon as the rank that deflates it has published how many bytes and records it made
+// (the segment ledger, pipeline.hpp); that rank then writes its records straight into the owner's archive with pwrite. The
+// exchange is two 16-byte entries per segment; the payload never crosses ranks.
 #include "pipeline.hpp"
 
 #include <algorithm>
@@ -45,6 +53,11 @@ struct Batch {
     bool segment = false;
     uint64_t seg_off = 0, seg_len = 0; // byte range of the file; a whole number of chunks unless it is the last segment
     bool seg_last = false;
+    int seg = 0;               // segment number inside the file
+    // who does what with a segment when the file is cut over several ranks: LOCAL = this rank deflates it and owns the archive;
+    // PLACE = this rank owns the archive, another rank deflates (the owner only hands out the place); REMOTE = this rank
+    // deflates for another rank's archive
+    enum Role { LOCAL, PLACE, REMOTE } role = LOCAL;
 };
 struct LoadedFile {
     const std::string *relpath;
@@ -53,9 +66,11 @@ struct LoadedFile {
 // a file that is cut into segments: its sequence ids continue across batches (the split rule may add records), and its
 // digest comes from the hasher thread
 struct BigFile {
-    size_t file = 0;
-    int next_seq = 0;                    // guarded by the commit order
-    std::shared_future<std::string> md5; // 32 hex characters ("" when the file could not be read)
+    size_t file = 0;                     // index into the rank's file list
+    int owner = 0;                       // rank whose archive holds the file
+    std::string key;                     // ledger key (same on every rank)
+    int next_seq = 0;                    // guarded by the commit order (owner only)
+    std::shared_future<std::string> md5; // 32 hex characters ("" when the file could not be read); owner only
 };
 
 // compression.cpp:73-104: i32 total_size, i32 path_len, path, i32 sequence_id, u8 is_last_chunk, payload[, 32 hex chars]
@@ -127,6 +142,7 @@ void merge_stats(const RunStats &s) {
 // shared by the workers of one do_compression call
 struct Job {
     const std::string &input_dir;
+    const std::string &output_dir;
     const std::vector<PlannedFile> &files;
     const std::vector<Batch> &batches;
     std::vector<BigFile> &bigs;
@@ -138,11 +154,14 @@ struct Job {
     std::atomic<size_t> next_batch{0};
     OrderedCommit order;
     uint64_t archive_off = 0; // guarded by the commit order
-    Job(const std::string &in, const std::vector<PlannedFile> &f, const std::vector<Batch> &b, std::vector<BigFile> &bg, int fd_, size_t cap_,
-        int level_, int device_)
-        : input_dir(in), files(f), batches(b), bigs(bg), fd(fd_), cap(cap_), out_cap(0), level(level_), device(device_) {
+    Job(const std::string &in, const std::string &out, const std::vector<PlannedFile> &f, const std::vector<Batch> &b, std::vector<BigFile> &bg, int fd_,
+        size_t cap_, int level_, int device_)
+        : input_dir(in), output_dir(out), files(f), batches(b), bigs(bg), fd(fd_), cap(cap_), out_cap(0), level(level_), device(device_) {
         size_t max_files = 1;
-        for (const auto &x : b) max_files = std::max(max_files, x.count);
+        for (const auto &x : b) {
+            max_files = std::max(max_files, x.count);
+            cap = std::max<size_t>(cap, (size_t) x.bytes);
+        }
         out_cap = cap + (cap / CHUNK_SIZE + max_files + 16) * 64 + 4096;
     }
 };
@@ -165,7 +184,9 @@ class Worker {
             size_t b = job_.next_batch.fetch_add(1);
             if (b >= job_.batches.size()) break;
             const Batch &batch = job_.batches[b];
-            if (batch.segment)
+            if (batch.segment && batch.role == Batch::PLACE)
+                place(b, batch, p);
+            else if (batch.segment)
                 segment(b, batch, p);
             else
                 small_files(b, batch, p);
@@ -366,23 +387,81 @@ class Worker {
             st.raw_bytes += batch.seg_len;
             st.t_write += now_seconds() - t0;
         }
-        commit(b, p, log, [&] {
-            // sequence ids continue where the previous segment stopped (they run ahead of the chunk index when the split rule
-            // fired earlier in the file): renumber in place, the id sits at a fixed place of every record header
-            const int base = big.next_seq;
-            int count = 0;
-            size_t o = 0;
-            while (o + 8 <= p.records.size()) {
+        if (batch.role == Batch::REMOTE) {
+            // another rank's archive: say what this segment came to, learn its place, write it there. Nothing of this enters
+            // this rank's own archive, so its turn in the commit order is passed on at once.
+            job_.order.wait_turn(b);
+            if (!log.empty()) std::cerr << log << std::flush;
+            job_.order.done(b);
+            uint32_t nrec = 0;
+            for (size_t o = 0; o + 8 <= p.records.size();) {
                 int total_size, path_length;
                 std::memcpy(&total_size, p.records.data() + o, 4);
                 std::memcpy(&path_length, p.records.data() + o + 4, 4);
-                int seq = base + count++;
-                std::memcpy(p.records.data() + o + 8 + path_length, &seq, 4);
                 const bool last = p.records[o + 12 + (size_t) path_length] != 0;
                 o += 4 + (size_t) total_size + (last ? MD5_DATA_SIZE : 0);
+                ++nrec;
             }
-            big.next_seq = base + count;
+            ledger_publish(job_.output_dir, big.key, batch.seg, ".size", p.records.size(), nrec);
+            uint64_t seq_base = 0;
+            const uint64_t at = ledger_wait(job_.output_dir, big.key, batch.seg, ".place", &seq_base);
+            renumber(p.records, (int) seq_base);
+            const std::string owner_archive = generate_output_filename(job_.output_dir, big.owner);
+            int ofd = ::open(owner_archive.c_str(), O_WRONLY);
+            if (ofd < 0) throw std::runtime_error("zwz: cannot open " + owner_archive);
+            double t1 = now_seconds();
+            write_at(ofd, p.records.data(), p.records.size(), at);
+            ::close(ofd);
+            st.t_write += now_seconds() - t1;
+            ledger_publish(job_.output_dir, big.key, batch.seg, ".done", p.records.size(), nrec);
+            merge_stats(st);
+            p.st = RunStats();
+            p.records.clear();
+            return; // nothing pending
+        }
+        commit(b, p, log, [&] {
+            // sequence ids continue where the previous segment stopped (they run ahead of the chunk index when the split rule
+            // fired earlier in the file): renumber in place, the id sits at a fixed place of every record header
+            big.next_seq += renumber(p.records, big.next_seq);
         });
+    }
+
+    // The owner's side of a segment another rank deflates: wait for its size, hand out its place, move on.
+    void place(size_t b, const Batch &batch, Pending &p) {
+        const PlannedFile &pf = job_.files[batch.first];
+        BigFile &big = job_.bigs[(size_t) pf.big];
+        p.records.clear();
+        p.md5_pos.clear();
+        p.ticket = 0;
+        p.has_big_md5 = false;
+        job_.order.wait_turn(b);
+        uint64_t nrec = 0;
+        const uint64_t bytes = ledger_wait(job_.output_dir, big.key, batch.seg, ".size", &nrec);
+        ledger_publish(job_.output_dir, big.key, batch.seg, ".place", job_.archive_off, (uint64_t) big.next_seq);
+        job_.archive_off += bytes;
+        big.next_seq += (int) nrec;
+        job_.order.done(b);
+        ledger_wait(job_.output_dir, big.key, batch.seg, ".done"); // the archive is complete only when the other rank has written
+        p.st.records += nrec;
+        p.st.raw_bytes += batch.seg_len;
+        merge_stats(p.st);
+        p.st = RunStats();
+    }
+
+    // sets the sequence ids of the serialised records to base, base + 1, ...; returns how many there are
+    static int renumber(std::vector<char> &records, int base) {
+        int count = 0;
+        size_t o = 0;
+        while (o + 8 <= records.size()) {
+            int total_size, path_length;
+            std::memcpy(&total_size, records.data() + o, 4);
+            std::memcpy(&path_length, records.data() + o + 4, 4);
+            int seq = base + count++;
+            std::memcpy(records.data() + o + 8 + path_length, &seq, 4);
+            const bool last = records[o + 12 + (size_t) path_length] != 0;
+            o += 4 + (size_t) total_size + (last ? MD5_DATA_SIZE : 0);
+        }
+        return count;
     }
 
     Job &job_;
@@ -404,12 +483,19 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         return;
     }
     std::string output_filename = generate_output_filename(output_dir, world_rank);
-    int fd = ::open(output_filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
-    if (fd < 0) {
-        std::cerr << "Rank: " << world_rank << " - Error opening archive: " << output_filename << std::endl;
-        return;
+    const int line_count = count_non_empty_lines(file_record);
+    // like the reference (main.cpp:47-52), a rank beyond the number of files writes no archive — but it may still deflate
+    // segments of a big file for another rank's archive
+    const bool has_archive = world_rank < line_count;
+    int fd = -1;
+    if (has_archive) {
+        fd = ::open(output_filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) {
+            std::cerr << "Rank: " << world_rank << " - Error opening archive: " << output_filename << std::endl;
+            return;
+        }
+        std::cout << "Max record line num: " << line_count << std::endl;
     }
-    std::cout << "Max record line num: " << count_non_empty_lines(file_record) << std::endl;
 
     // the device comes up while the files are dealt and sized
     std::exception_ptr warm_error;
@@ -420,47 +506,89 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
             warm_error = std::current_exception();
         }
     });
-    // the deal, then the plan, in deal order
-    std::vector<PlannedFile> files;
-    int file_number = 0, next_file_number = world_rank;
-    std::string file_path;
-    while (std::getline(record_file, file_path)) {
-        if (file_number == next_file_number) {
-            next_file_number += cfg.world_size;
-            files.push_back({file_path, 0, -1});
-        }
-        file_number++;
+    // the deal (compression.cpp:31-41), then the plan, in deal order
+    std::vector<std::string> lines;
+    {
+        std::string file_path;
+        while (std::getline(record_file, file_path)) lines.push_back(file_path);
     }
-    parallel_for(files.size(), io_threads() * 2, [&](size_t i) {
+    const int file_number = (int) lines.size();
+    const int world = std::max(1, cfg.world_size);
+    std::vector<PlannedFile> files;
+    for (size_t i = (size_t) world_rank; i < lines.size(); i += (size_t) world) files.push_back({lines[i], 0, -1});
+    const size_t n_own = files.size();
+    auto size_of = [&](const std::string &rel) {
         std::error_code ec;
-        uint64_t size = fs::file_size(fs::path(input_dir) / files[i].relpath, ec);
-        files[i].size = ec ? 0 : size;
-    });
+        uint64_t size = fs::file_size(fs::path(input_dir) / rel, ec);
+        return ec ? (uint64_t) 0 : size;
+    };
+    parallel_for(n_own, io_threads() * 2, [&](size_t i) { files[i].size = size_of(files[i].relpath); });
     uint64_t total_bytes = 0;
     for (const auto &f : files) total_bytes += f.size;
     // batches small enough that every worker gets several (a 200 MB job in one 128 MB batch would leave the pool idle)
     const int pool = worker_count();
     const size_t cap = (size_t) std::min<uint64_t>(cfg.batch_bytes, std::max<uint64_t>((uint64_t) 8 << 20, total_bytes / ((uint64_t) pool * 3) + 1));
-    const uint64_t seg_bytes = std::max<uint64_t>(1, cap / CHUNK_SIZE) * CHUNK_SIZE; // whole chunks
+    // Files larger than a batch (cfg.batch_bytes: the same on every rank) are cut into segments of whole chunks. The record
+    // is size-descending, so the run's big files are its first lines: every rank finds the same list.
+    const uint64_t seg_bytes = std::max<uint64_t>(1, cfg.batch_bytes / CHUNK_SIZE) * CHUNK_SIZE;
+    struct RunBig {
+        size_t line;
+        uint64_t size;
+    };
+    std::vector<RunBig> run_bigs;
+    for (size_t gi = 0; gi < lines.size(); ++gi) {
+        const uint64_t size = (int) (gi % (size_t) world) == world_rank ? files[gi / (size_t) world].size : (world > 1 ? size_of(lines[gi]) : 0);
+        if (size + 64 <= cfg.batch_bytes) break;
+        run_bigs.push_back({gi, size});
+    }
     std::vector<Batch> batches;
     std::vector<BigFile> bigs;
-    for (size_t i = 0; i < files.size(); ++i) {
-        if (files[i].size + 64 > cap) {
+    auto segments_of = [&](size_t file_index, int big_index, uint64_t size, int owner, bool mine_is_owner) {
+        const int nseg = (int) (size / seg_bytes) + 1; // the last segment carries the tail chunk (possibly empty)
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            const bool last = sgi == nseg - 1;
+            const int worker_rank = (last || world == 1) ? owner : (owner + sgi) % world; // the digest travels with the last one
+            Batch b;
+            b.first = file_index;
+            b.count = 1;
+            b.segment = true;
+            b.seg = sgi;
+            b.seg_off = (uint64_t) sgi * seg_bytes;
+            b.seg_len = last ? size - b.seg_off : seg_bytes;
+            b.bytes = b.seg_len;
+            b.seg_last = last;
+            if (mine_is_owner)
+                b.role = worker_rank == world_rank ? Batch::LOCAL : Batch::PLACE;
+            else if (worker_rank == world_rank)
+                b.role = Batch::REMOTE;
+            else
+                continue;
+            if (b.role == Batch::PLACE) b.bytes = 0;
+            batches.push_back(b);
+        }
+        (void) big_index;
+    };
+    // segments this rank deflates for other ranks' archives come first: their owners are waiting for the sizes
+    for (const auto &rb : run_bigs) {
+        const int owner = (int) (rb.line % (size_t) world);
+        if (owner == world_rank) continue;
+        files.push_back({lines[rb.line], rb.size, (int) bigs.size()});
+        BigFile bf;
+        bf.file = files.size() - 1;
+        bf.owner = owner;
+        bf.key = "c" + std::to_string(rb.line) + "_" + cfg.run_id;
+        bigs.push_back(bf);
+        segments_of(files.size() - 1, (int) bigs.size() - 1, rb.size, owner, false);
+    }
+    for (size_t i = 0; i < n_own; ++i) {
+        if (files[i].size + 64 > cfg.batch_bytes) {
             files[i].big = (int) bigs.size();
-            bigs.push_back({i, 0, {}});
-            for (uint64_t o = 0;; o += seg_bytes) {
-                const bool last = files[i].size - o < seg_bytes; // the last segment carries the tail chunk (possibly empty)
-                Batch s;
-                s.first = i;
-                s.count = 1;
-                s.segment = true;
-                s.seg_off = o;
-                s.seg_len = last ? files[i].size - o : seg_bytes;
-                s.bytes = s.seg_len;
-                s.seg_last = last;
-                batches.push_back(s);
-                if (last) break;
-            }
+            BigFile bf;
+            bf.file = i;
+            bf.owner = world_rank;
+            bf.key = "c" + std::to_string((size_t) world_rank + i * (size_t) world) + "_" + cfg.run_id;
+            bigs.push_back(bf);
+            segments_of(i, files[i].big, files[i].size, world_rank, true);
             continue;
         }
         if (batches.empty() || batches.back().segment || batches.back().bytes + files[i].size > cap || batches.back().count >= 262144) {
@@ -471,10 +599,19 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         batches.back().count++;
         batches.back().bytes += files[i].size;
     }
+    if (world > 1 && !run_bigs.empty()) {
+        std::error_code ec;
+        fs::create_directories(ledger_dir(output_dir), ec);
+    }
 
+    if (batches.empty() && !has_archive) { // nothing of its own and nothing to do for the others
+        warm.join();
+        std::cout << "Rank: " << world_rank << " - No file to compress" << std::endl;
+        return;
+    }
     warm.join();
     if (warm_error) {
-        ::close(fd);
+        if (fd >= 0) ::close(fd);
         std::rethrow_exception(warm_error);
     }
     // hashers for the files that are cut into segments (at most 4 at a time; each streams its file once more through the GPU)
@@ -487,6 +624,10 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
             for (;;) {
                 size_t k = next_big.fetch_add(1);
                 if (k >= bigs.size()) return;
+                if (bigs[k].owner != world_rank) { // another rank's file: its owner hashes it
+                    promises[k].set_value("");
+                    continue;
+                }
                 try {
                     promises[k].set_value(hash_big_file(cfg.device, (int) h, input_dir + "/" + files[bigs[k].file].relpath));
                 } catch (...) {
@@ -494,7 +635,7 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
                 }
             }
         });
-    Job job(input_dir, files, batches, bigs, fd, std::max<size_t>(cap, (size_t) seg_bytes), cfg.level, cfg.device);
+    Job job(input_dir, output_dir, files, batches, bigs, fd, cap, cfg.level, cfg.device);
     const int workers = (int) std::min<size_t>((size_t) pool, std::max<size_t>(1, batches.size()));
     std::exception_ptr failure;
     try {
@@ -506,8 +647,22 @@ void do_compression(const std::string &input_dir, const std::string &output_dir,
         failure = std::current_exception();
     }
     for (auto &t : hashers) t.join();
-    ::close(fd);
+    if (fd >= 0) ::close(fd);
     if (failure) std::rethrow_exception(failure);
+    if (world > 1) { // this rank's ledger entries have served their purpose (every PLACE waited for its segment's .done)
+        std::error_code ec;
+        for (const auto &bf : bigs) {
+            if (bf.owner != world_rank) continue;
+            const int nseg = (int) (files[bf.file].size / seg_bytes) + 1;
+            for (int sg = 0; sg < nseg; ++sg)
+                for (const char *what : {".size", ".place", ".done"}) fs::remove(ledger_dir(output_dir) + "/" + bf.key + "." + std::to_string(sg) + what, ec);
+        }
+        fs::remove(ledger_dir(output_dir), ec); // succeeds once the last owner has cleaned up
+    }
+    if (!has_archive) {
+        std::cout << "Rank: " << world_rank << " - No file to compress" << std::endl;
+        return;
+    }
     std::cout << "Rank: " << world_rank << " - Total processed file: " << file_number << std::endl;
     print_timing("compress");
 }

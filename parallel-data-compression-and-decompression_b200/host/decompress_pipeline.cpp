@@ -304,34 +304,6 @@ struct Job {
     bool mine(size_t g) const { return world <= 1 || (int) (g % (size_t) world) == rank; }
 };
 
-std::string ledger_dir(const std::string &output_dir) { return output_dir + "/.zwz_segments"; }
-
-// raw size of segment `seg` of file `key`, published by whichever rank inflated it
-void ledger_publish(const std::string &output_dir, const std::string &key, int seg, const char *what, uint64_t value) {
-    const std::string final_name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
-    const std::string tmp = final_name + ".tmp" + std::to_string((long) getpid());
-    std::FILE *f = std::fopen(tmp.c_str(), "wb");
-    if (!f) throw std::runtime_error("zwz: cannot write the segment ledger");
-    std::fwrite(&value, 8, 1, f);
-    std::fclose(f);
-    if (std::rename(tmp.c_str(), final_name.c_str()) != 0) throw std::runtime_error("zwz: cannot publish to the segment ledger");
-}
-uint64_t ledger_wait(const std::string &output_dir, const std::string &key, int seg, const char *what) {
-    const std::string name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
-    const double t0 = now_seconds();
-    for (;;) {
-        std::FILE *f = std::fopen(name.c_str(), "rb");
-        if (f) {
-            uint64_t v = 0;
-            size_t k = std::fread(&v, 8, 1, f);
-            std::fclose(f);
-            if (k == 1) return v;
-        }
-        if (now_seconds() - t0 > 900.0) throw std::runtime_error("zwz: timed out waiting for segment " + std::to_string(seg) + " of " + key + " from another rank");
-        usleep(500);
-    }
-}
-
 class Worker {
   public:
     Worker(Job &job, int id) : job_(job), ctx_(worker_ctx(job.device, id)), in_(ctx_), out_(ctx_) {}
@@ -690,7 +662,7 @@ void do_decompression(const std::string &input_dir, const std::string &output_di
                 big->archive = ai;
                 big->file = fi;
                 big->path = output_dir + "/" + files[fi].relpath;
-                big->key = "a" + std::to_string(ai) + "f" + std::to_string(fi);
+                big->key = "a" + std::to_string(ai) + "f" + std::to_string(fi) + "_" + cfg.run_id;
                 const size_t nrec = files[fi].ordered.size();
                 for (size_t r0 = 0; r0 < nrec; r0 += per_seg) {
                     Group g;

@@ -95,7 +95,7 @@ static int compress(const std::string &folder_path, const std::string &output_pa
     std::cout << "file_record: " << file_record << std::endl;
     timing_mark("file record ready");
     int file_count = count_non_empty_lines(file_record);
-    if (cfg.world_rank < file_count) {
+    if (cfg.world_rank < file_count || cfg.world_size > 1) { // a rank without files of its own may still deflate segments of a big file
         do_compression(folder_path, output_path, file_record, cfg.world_rank);
     } else {
         std::cout << "Rank: " << cfg.world_rank << " - No file to compress" << std::endl;
@@ -203,14 +203,15 @@ int main(int argc, char *argv[]) {
     const bool compressing = operation == "compress";
     const bool decompressing = operation == "decompress";
     if (const char *id = std::getenv("ZWZ_RUN_ID")) g_run_id = id;
+    cfg.run_id = g_run_id;
     if (cfg.world_rank == 0) {
         if (!prepare_paths(source_path, output_path)) return 1;
         if (compressing) { // whatever an earlier run left
             std::remove((output_path + kReadyMarker).c_str());
             for (int r = 1; r < std::max(cfg.world_size, 64); ++r) std::remove((output_path + kReadyMarker + ".ack" + std::to_string(r)).c_str());
         }
-        if (decompressing) {
-            std::error_code ec;
+        if (cfg.world_size == 1 || g_run_id.empty()) { // the segment ledger of an earlier run (a launcher with ZWZ_RUN_ID may
+            std::error_code ec;                        // already have ranks at work in it)
             std::filesystem::remove_all(output_path + "/.zwz_segments", ec);
         }
     }
@@ -219,6 +220,7 @@ int main(int argc, char *argv[]) {
     std::vector<pid_t> kids;
     if (self_gpus > 1 && (compressing || decompressing)) {
         if (g_run_id.empty()) g_run_id = "self-" + std::to_string((long) getpid()) + "-" + std::to_string((long long) (start_time * 1e6));
+        cfg.run_id = g_run_id;
         kids = fork_ranks(self_gpus);
     }
 

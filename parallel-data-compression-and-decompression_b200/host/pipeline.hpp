@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
+#include <unistd.h>
 #include <exception>
 #include <functional>
 #include <mutex>
@@ -106,6 +108,42 @@ template <class F> inline void parallel_for(size_t n, int threads, F &&fn) {
     for (size_t t = 1; t < nt; ++t) ts.emplace_back(body);
     body();
     for (auto &t : ts) t.join();
+}
+
+// ---- the segment ledger: how the ranks of one run tell each other a few numbers about the segments of a file that is cut
+// over several GPUs (sizes, offsets). Tiny files under <output dir>/.zwz_segments/, published with write + rename (a reader
+// sees all of an entry or none) and polled by the ranks that need them — the same shared-directory channel the ranks use for
+// the file record (main.cpp); the reference's ranks exchange nothing but that path either (main.cpp:27-35). The `.zwz`
+// format itself has no index to exchange: what the ranks need from each other is where a segment's records go.
+inline std::string ledger_dir(const std::string &output_dir) { return output_dir + "/.zwz_segments"; }
+inline void ledger_publish(const std::string &output_dir, const std::string &key, int seg, const char *what, uint64_t a, uint64_t b = 0) {
+    const std::string final_name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
+    const std::string tmp = final_name + ".tmp" + std::to_string((long) getpid());
+    std::FILE *f = std::fopen(tmp.c_str(), "wb");
+    if (!f) throw std::runtime_error("zwz: cannot write the segment ledger");
+    uint64_t v[2] = {a, b};
+    std::fwrite(v, 8, 2, f);
+    std::fclose(f);
+    if (std::rename(tmp.c_str(), final_name.c_str()) != 0) throw std::runtime_error("zwz: cannot publish to the segment ledger");
+}
+inline uint64_t ledger_wait(const std::string &output_dir, const std::string &key, int seg, const char *what, uint64_t *b = nullptr) {
+    const std::string name = ledger_dir(output_dir) + "/" + key + "." + std::to_string(seg) + what;
+    const double t0 = now_seconds();
+    for (;;) {
+        std::FILE *f = std::fopen(name.c_str(), "rb");
+        if (f) {
+            uint64_t v[2] = {0, 0};
+            size_t k = std::fread(v, 8, 2, f);
+            std::fclose(f);
+            if (k == 2) {
+                if (b) *b = v[1];
+                return v[0];
+            }
+        }
+        if (now_seconds() - t0 > 900.0)
+            throw std::runtime_error("zwz: timed out waiting for segment " + std::to_string(seg) + " of " + key + " from another rank");
+        usleep(500);
+    }
 }
 
 // grow-only page-locked host buffer (copies from/to it run at full PCIe speed and asynchronously)

@@ -39,6 +39,7 @@ struct RunConfig {
     bool verify_all = false;  // also print an MD5 verdict for files whose last record arrived out of order
     bool strict = false;      // ZWZ_STRICT=1: name every record that did not decode to a clean end of stream, exit code 4
                               // (the reference ignores zlib's return codes, decompression.cpp:31 — and so does the default)
+    std::string run_id;       // ZWZ_RUN_ID or the nonce of a self-launch: keys the files the ranks of one run leave for each other
     bool quarantine = false;  // ZWZ_QUARANTINE=1: move files whose MD5 does not match to <output dir>/bad/ (README.md:175,186 promises
                               // it; the reference's code leaves them in place, and so does the default)
     std::size_t batch_bytes = (std::size_t) 128 << 20; // per worker (ZWZ_BATCH_MB)

@@ -324,6 +324,48 @@ def test_multi_rank_decompress(main_bin, tmp_path, launch):
     same_tree(src, out)
 
 
+@needs_ref
+@pytest.mark.parametrize("launch", ["self", "ranks"])
+def test_one_file_cut_over_the_ranks_lands_in_one_archive(main_bin, tmp_path, launch):
+    """BASELINE config 3 / SURVEY.md §8(e): the reference's deal is file-granular (compression.cpp:31-41) and its reader wants
+    all records of a path in ONE archive (decompression.cpp:52-55). A file that is cut into segments is deflated by several
+    ranks here; the owner hands out archive offsets and sequence ids through the segment ledger and every rank writes its
+    records into the owner's archive. The unmodified reference reads the result back."""
+    src = tmp_path / "w" / "src"
+    src.mkdir(parents=True)
+    specs = [corpus.FileSpec("big/huge.log", 5_300_000, "T", 997), corpus.FileSpec("big/second.bin", 2_500_000, "S", 996),
+             corpus.FileSpec("small/a.txt", 70_000, "T", 995), corpus.FileSpec("small/r.bin", 140_000, "R", 994)]
+    corpus.write_tree(str(src), specs, 603)
+    arch, out = str(tmp_path / "arch"), str(tmp_path / "out")
+    if launch == "self":
+        run([main_bin, "compress", str(src), arch], {"ZWZ_GPUS": "3", "ZWZ_BATCH_MB": "1"})
+    else:
+        env = {**os.environ, "ZWZ_WORLD": "3", "ZWZ_BATCH_MB": "1", "ZWZ_RUN_ID": "c3"}
+        procs = [subprocess.Popen([main_bin, "compress", str(src), arch], env={**env, "ZWZ_RANK": str(r)}, stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in (2, 1, 0)]
+        for p in procs:
+            o = p.communicate()[0]
+            assert p.returncode == 0, o[-2000:]
+    assert sorted(f for f in os.listdir(arch)) == ["compressed_0.zwz", "compressed_1.zwz", "compressed_2.zwz"]   # ledger and marker are gone
+    owner = {}
+    for r in range(3):
+        recs = zwz_format.parse(open(os.path.join(arch, f"compressed_{r}.zwz"), "rb").read())
+        by = {}
+        for rec in recs:
+            by.setdefault(rec.path, []).append(rec)
+        for pth, rs in by.items():
+            assert pth not in owner                                          # all records of a path in one archive
+            owner[pth] = r
+            assert [x.seq for x in rs] == list(range(len(rs)))               # contiguous ids, in order
+            assert [x.last for x in rs] == [False] * (len(rs) - 1) + [True]
+            assert rs[-1].md5.decode() == hashlib.md5(open(os.path.join(str(src), pth), "rb").read()).hexdigest()
+    order = sorted(specs, key=lambda s_: -s_.size)
+    assert owner == {s_.relpath: i % 3 for i, s_ in enumerate(order)}       # the reference's deal decides the archive
+    dlog = run([MAIN_REF, "decompress", arch, out])
+    assert dlog.count("MD5 match for file") == len(specs) and "mismatch" not in dlog
+    same_tree(str(src), out)
+
+
 def test_usage_and_errors(main_bin, tmp_path):
     r = subprocess.run([main_bin, "compress"], capture_output=True, text=True)
     assert r.returncode != 0 and "Usage:" in r.stderr

@@ -374,6 +374,44 @@ def test_deflate_ratio_within_tolerance_of_zlib6(ctx, is_gpu):
         assert sum(sizes) <= RATIO_TOLERANCE * z, (cls, sum(sizes), z)
 
 
+def test_deflate_stored_regions_inside_a_chunk(ctx, is_gpu):
+    """Incompressible stretches inside a compressible chunk go out as stored blocks between Huffman blocks (the encoder finds them
+    from the match kernel's tile flags, at 1 024-byte granularity). Boundaries at every offset around the 1 024-byte marks, matches
+    right behind the stretch, stretches at the start / end of the chunk: the streams must inflate to the input (zlib and oracle)
+    and be no larger than zlib's."""
+    text = corpus.gen_text(40000, 596, 71).tobytes()
+    rnd = corpus.gen_random(40000, 596, 72).tobytes()
+    chunks = []
+    step = 1 if is_gpu else 5
+    for d in range(-36, 37, step):
+        a, k = 2048 + d, 3072 - d // 2
+        chunks.append(text[:a] + rnd[:k] + text[a:a + 3000])            # text | random | text
+        chunks.append(rnd[:k] + text[:2000] + text[:2000])                # random first, then text that repeats at once
+        chunks.append(text[:a] + text[:a][-700:] + rnd[:k])               # random last
+        chunks.append(text[:1000 + d] + rnd[:1024] + text[:1500] + rnd[2000:3100 + d] + text[:900])   # two short stretches
+        chunks.append(text[:2000] + rnd[:2096 + d] + text[:2000])        # a long match starts right behind the stretch, d bytes off a 1 024 mark
+        chunks.append(text[:2000] + rnd[:3120 + d] + text[500:2000])
+    for j in range(0, 40, 1 if is_gpu else 3):   # a lone match planted j bytes behind a 1 024-byte mark inside a random stretch
+        c = bytearray(rnd[:7000])
+        c[3072 + j:3072 + j + 5] = c[100:105]
+        c[5120 + j:5120 + j + 40] = c[200:240]
+        chunks.append(text[:700] + bytes(c))
+    chunks.append(text[:20000] + rnd[:25000] + text[:20000])
+    chunks.append(rnd[:30000] + b"\x00" * 5000 + rnd[:30000])
+    raw, off = _cat(chunks)
+    packed, poff, res = ctx.deflate_batch(raw, off[:-1], np.diff(off).astype(np.uint32))
+    ours = zl = 0
+    for i, c in enumerate(chunks):
+        p = packed[int(poff[i]):int(poff[i + 1])].tobytes()
+        assert int(res["len1"][i]) == 0
+        assert zlib.decompress(p) == c, i
+        back, st, _ = O.inflate(p, 70000)
+        assert st == O.STREAM_END and back == c, i
+        ours += len(p)
+        zl += len(zlib.compress(c, 6))
+    assert ours <= zl, (ours, zl)   # a stored stretch costs 5 bytes; zlib pays 8-bit-plus literals for it
+
+
 def test_deflate_length_limited_codes(ctx):
     """Fibonacci-like symbol frequencies push the unrestricted Huffman depth past 15 bits (and the code-length code past
     7): the length-limiting repair has to leave a complete, decodable code."""

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 fifth GPU pass: deflate traffic cuts (tile flags, list discard), per-kernel DRAM traffic of one step, CLI with the tuned defaults
-O=gpurun_out/r2e
+O=gpurun_out/r2f
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $O/pytest_gpu.log
 timeout 900 python bench.py --steps 5 > $O/bench_c2.json 2> $O/bench_c2.err; echo "c2 exit $?" >> $O/bench_c2.err
@@ -35,6 +35,6 @@ tail -3 $O/pytest_gpu.log; cat $O/traffic.txt | head -40; python - <<'PY'
 import json
 for f in ("bench_c2","bench_c3"):
     try:
-        d=json.load(open(f"gpurun_out/r2e/{f}.json")); print(f, d["value"], d["e2e"]["value"], d["kernel_ms_per_step"], d.get("inflate_gbs"), d.get("deflate_gbs"), d.get("ratio"), d.get("size_vs_zlib6"))
+        d=json.load(open(f"gpurun_out/r2f/{f}.json")); print(f, d["value"], d["e2e"]["value"], d["kernel_ms_per_step"], d.get("inflate_gbs"), d.get("deflate_gbs"), d.get("ratio"), d.get("size_vs_zlib6"))
     except Exception as e: print(f, "ERR", e)
 PY
