@@ -571,6 +571,28 @@ ZWZ_DEV_NOINLINE uint32_t enc_find_stored_regions(const uint32_t *m, uint32_t n,
     const unsigned q1 = __ballot_sync(ZWZ_FULL, lane + 32u < nkb && __popc(S.tflags[lane + 32u]) <= ZWZ_DE_QUIET_TILES);
     uint64_t quiet = (uint64_t) q0 | ((uint64_t) q1 << 32);
     uint32_t nreg = 0;
+    if (quiet == 0ull) return 0u;
+    // an unset mark takes the next set one (the end of the chunk behind the last): "first step at or behind this stretch"
+    if (lane == 0) {
+        uint32_t t = ntok, q = n, te = ntok, qe = n;
+        for (int k = 64; k >= 0; --k) {
+            if (S.kb_tok[k] == 0xffffu) {
+                S.kb_tok[k] = (uint16_t) t;
+                S.kb_pos[k] = (uint16_t) q;
+            } else {
+                t = S.kb_tok[k];
+                q = S.kb_pos[k];
+            }
+            if (S.kb_end[k] == 0xffffu) {
+                S.kb_end[k] = (uint16_t) te;
+                S.kb_endpos[k] = (uint16_t) qe;
+            } else {
+                te = S.kb_end[k];
+                qe = S.kb_endpos[k];
+            }
+        }
+    }
+    __syncwarp();
     while (quiet && nreg < 4u) { // warp-uniform
         const uint32_t a = (uint32_t) __ffsll((long long) quiet) - 1u;
         uint64_t rest = ~(quiet >> a); // first zero above a ends the run
@@ -719,6 +741,13 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
     }
     __syncwarp();
 #define ENC_WORD_AT(x_) ((x_) < n ? (((S.tflags[(x_) >> 10] >> (((x_) >> 5) & 31u)) & 1u) ? m[(x_)] : ((uint32_t) src[(x_)] << 24)) : 0u)
+    // marks of stretches in which no step starts (resp. into which none reaches first) stay "unset" and are resolved later — the
+    // last, partial stretch of a chunk is the usual case
+    for (uint32_t i = lane; i < 66u; i += 32u) {
+        S.kb_tok[i] = 0xffffu;
+        S.kb_end[i] = 0xffffu;
+    }
+    __syncwarp();
     uint32_t ntok = 0;
     uint32_t last_kb = 0xffffffffu, last_kbe = 0xffffffffu;
     uint64_t extra_bits = 0; // length + distance extra bits of all matches (lane-partial, summed later)

@@ -210,6 +210,17 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, std::function<void
     for (unsigned b = 0; b < grid; ++b) {
         blockIdx = {b, 0, 0};
         memset(s.dyn, 0xA5, smem_bytes + 1024); // smem is garbage at CTA start on real hardware too
+        // ZWZ_EMU_POISON=<seed>: garbage that LOOKS like data (small 16-bit values, as the previous kernel's position lists
+        // leave behind on the device) — 0xA5A5 is out of range for most indices and hides reads of unset state
+        if (const char *ps = getenv("ZWZ_EMU_POISON")) {
+            static uint64_t launches = 0;
+            uint64_t x = (strtoull(ps, nullptr, 0) + 1000u * ++launches) * 0x9E3779B97F4A7C15ull + b + 1;
+            uint16_t *w = (uint16_t *) s.dyn;
+            for (size_t k = 0; k < smem_bytes / 2; ++k) {
+                x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+                w[k] = (uint16_t) ((x >> 20) % 6000u);
+            }
+        }
         s.exited = 0;
         s.bar_count = 0;
         s.stall = 0;

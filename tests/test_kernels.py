@@ -432,6 +432,29 @@ def test_deflate_length_limited_codes(ctx):
     _deflate_and_verify(ctx, chunks)
 
 
+def test_deflate_short_last_stretch_unset_marks(ctx, is_gpu, monkeypatch):
+    """A chunk a few bytes longer than a multiple of 1 024 ends in a stretch no parse step STARTS in: its stored-region marks
+    must read as "end of chunk", not as whatever the shared memory held (on the device: the match kernel's position lists —
+    the emulator fills shared memory with such look-alike values under ZWZ_EMU_POISON). Regression: ~1 in 10^4 C2 files
+    came out as a stream that stopped short."""
+    monkeypatch.setenv("ZWZ_EMU_POISON", "11")
+    text = corpus.gen_text(9000, 596, 81).tobytes()
+    rnd = corpus.gen_random(9000, 596, 82).tobytes()
+    mixed = bytes(a if i % 3 else b for i, (a, b) in enumerate(zip(text, rnd)))   # matches in every tile, few of them long
+    for rep in range(6 if is_gpu else 12):
+        chunks = []
+        for kb in (1, 2, 4, 5):
+            for extra in (1, 2, 7, 17, 31, 33, 77):
+                n = 1024 * kb + extra
+                chunks.append(mixed[rep:rep + n])
+                chunks.append(text[rep:rep + n - 40] + rnd[:40])
+                chunks.append(text[:300] + rnd[rep:rep + n - 300])
+        raw, off = _cat(chunks)
+        packed, poff, res = ctx.deflate_batch(raw, off[:-1], np.diff(off).astype(np.uint32))
+        for i, c in enumerate(chunks):
+            assert zlib.decompress(packed[int(poff[i]):int(poff[i + 1])].tobytes()) == c, (rep, i, len(c))
+
+
 def test_deflate_many_small_chunks(ctx, is_gpu):
     """C2-shaped stress: every stream must decode under the reference's zlib (this is the test that caught an
     over-subscribed code-length code)."""
