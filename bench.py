@@ -341,6 +341,9 @@ def records_of(res, poff, raw_off):
     return r_off, r_len, np.concatenate([r_raw, raw_off[-1:]]), k
 
 
+CALL_WALL = {"compress": 0.0, "decompress": 0.0, "parts": 0}   # --e2e-profile: seconds inside the two plugin calls, summed over parts
+
+
 def host_roundtrip(w, d, clen, raw_ptr, comp_ptr, comp_cap, back_ptr, level, do_md5):
     """One part of the shard through the host-buffer plugin calls (what `main` does per batch): compress side into the
     buffer at comp_ptr, then the decompress side from that buffer into back_ptr. Returns the compressed bytes."""
@@ -348,12 +351,19 @@ def host_roundtrip(w, d, clen, raw_ptr, comp_ptr, comp_cap, back_ptr, level, do_
     if "foff" in d:
         nfp = d["f1"] - d["f0"]
         # compress side: compression.cpp:106-148 for the files of this part (chunking, deflate, MD5 of every file)
+        t0 = time.perf_counter()
         poff, res, dg1 = w.compress_files_into(raw_ptr, d["foff"], level, comp_ptr, comp_cap, want_md5=do_md5)
+        t1 = time.perf_counter()
         # decompress side: decompression.cpp:100-151 for the records just made
         r_off, r_len, _, k = records_of(res, poff, np.zeros(c1 - c0 + 1, dtype=np.uint64))
         rfile = d["rfile"] if k is None else np.insert(d["rfile"], k + 1, d["rfile"][k])
         rcap = np.full(len(r_off), CHUNK, dtype=np.uint32)
+        t2 = time.perf_counter()
         foff2, rl, st, dg2 = w.decompress_records_into(comp_ptr, r_off, r_len, rcap, rfile, nfp, back_ptr, b1 - b0, want_md5=do_md5)
+        t3 = time.perf_counter()
+        CALL_WALL["compress"] += t1 - t0
+        CALL_WALL["decompress"] += t3 - t2
+        CALL_WALL["parts"] += 1
         assert np.array_equal(foff2, d["foff"]), "file layout after decompress"
         if do_md5:
             assert np.array_equal(dg1, dg2), "MD5 verify failed"
@@ -471,6 +481,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg (its line then carries e2e = null)")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C1/C3-shaped device passes of the default c2 line")
     ap.add_argument("--e2e-workers", type=int, default=0, help="end-to-end leg: worker contexts (stream + buffers each) per rank; 0 = min(6, host cores / ranks), at least 2")
+    ap.add_argument("--e2e-profile", action="store_true", help="diagnostics for the end-to-end leg: wall time of the two plugin calls per part and "
+                    "the workers' kernel spans (CUDA events; spans of concurrently running kernels overlap, so their sum is an upper bound)")
     ap.add_argument("--e2e-parts", type=int, default=32, help="end-to-end leg: parts the shard is cut into")
     ap.add_argument("--md5", default="auto", choices=["auto", "on", "off"],
                     help="auto: on for c2/c1/c5 (compress+decompress+MD5 verify), off for c3 (BASELINE.json config 3 is deflate+inflate only: "
@@ -625,19 +637,35 @@ def main():
     comp_bytes = [0] * nparts
     part_desc = part_descriptors(sh, coff, clen, cfile, raw_off, slot_off, part_chunk, part_file, wrap)
 
+    def run_part(i, wi):
+        d = part_desc[i]
+        cap = int(slot_off[d["c1"]] - slot_off[d["c0"]]) + 64
+        hc = wi * comp_stride if sh.periodic else d["hc"]
+        hb = wi * back_stride if sh.periodic else d["y0"]
+        comp_bytes[i] = host_roundtrip(workers[wi], d, clen, hr_ptr + d["y0"], hc_ptr + hc, cap, hb_ptr + hb, args.level, do_md5)
+        last_part[wi] = i
+
     def e2e_part(i):
         with wlock:
             wi = wfree.pop()
         try:
-            d = part_desc[i]
-            cap = int(slot_off[d["c1"]] - slot_off[d["c0"]]) + 64
-            hc = wi * comp_stride if sh.periodic else d["hc"]
-            hb = wi * back_stride if sh.periodic else d["y0"]
-            comp_bytes[i] = host_roundtrip(workers[wi], d, clen, hr_ptr + d["y0"], hc_ptr + hc, cap, hb_ptr + hb, args.level, do_md5)
-            last_part[wi] = i
+            run_part(i, wi)
         finally:
             with wlock:
                 wfree.append(wi)
+
+    def size_workers():
+        """Warm-up: EVERY worker context takes the parts with the most chunks, files, raw bytes and slot bytes once, so that its
+        device and page-locked arenas have their final size before the timed steps (`main` sizes its workers' buffers from the
+        batch plan the same way). Parts are handed to whichever worker is free, so without this a worker can meet its largest part
+        inside the timed region — and growing a page-locked arena synchronises the whole device, for every worker."""
+        key = [lambda i: part_chunk[i + 1] - part_chunk[i], lambda i: part_b0[i + 1] - part_b0[i],
+               lambda i: int(slot_off[part_chunk[i + 1]] - slot_off[part_chunk[i]])]
+        if part_file is not None:
+            key.append(lambda i: part_file[i + 1] - part_file[i])
+        sizing = sorted({max(range(nparts), key=k) for k in key})
+        with ThreadPoolExecutor(W) as sp:
+            list(sp.map(lambda wi: [run_part(i, wi) for i in sizing], range(W)))
 
     pool = ThreadPoolExecutor(W)
 
@@ -682,10 +710,16 @@ def main():
     # e2e
     e2e_ms, e2e_launches = float("nan"), 0
     if not args.no_e2e:
+        size_workers()
         for _ in range(2):
             e2e_step()
         barrier()
         wl0 = sum(w.launches for w in workers)
+        if args.e2e_profile:
+            for w in workers:
+                w.profile_enable(True)
+                w.profile_read(True)
+            CALL_WALL.update(compress=0.0, decompress=0.0, parts=0)
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
         for _ in range(args.steps):
@@ -694,6 +728,14 @@ def main():
         barrier()
         e2e_ms = e2.elapsed_time(e3)
         e2e_launches = sum(w.launches for w in workers) - wl0
+        if args.e2e_profile:
+            wk = {}
+            for w in workers:
+                for k, v in w.profile_read(True).items():
+                    wk[k] = wk.get(k, 0.0) + v[0] / args.steps
+                w.profile_enable(False)
+            state["e2e_profile"] = {"worker_kernel_span_ms_per_step": wk, "call_wall_ms_per_part": {k: 1e3 * CALL_WALL[k] / max(CALL_WALL["parts"], 1) for k in ("compress", "decompress")},
+                                    "parts_per_step": nparts, "workers": W}
     clocks = sampler.stop()
     if args.no_e2e:
         pass
@@ -762,6 +804,8 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
+        if "e2e_profile" in state:
+            line["e2e_profile"] = state["e2e_profile"]
         # free the big buffers before the extra passes / CPU leg
         if args.workload == "c2" and not args.no_extra and world == 1:
             extra = {}

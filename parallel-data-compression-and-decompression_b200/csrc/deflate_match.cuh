@@ -288,6 +288,17 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
 
         // ---- 6. search: one lane per position, 32-position tiles ----
+        // Every lane walks the chain of its position: the cheap test (the two bytes that would extend its best match — zlib's
+        // longest_match order) turns most candidates away; a survivor is compared against the first 12 bytes of the scan string,
+        // which the lane holds in three registers, in straight-line code (three XORs and a find-first-set: no loop for the
+        // short matches that make up text), and by words beyond that. When the walks are done the lanes INHERIT: a match (L, d)
+        // at position j is a match (L - k, d) at j + k, so a prefix maximum of L_j + j over the tile (5 shuffle steps) hands
+        // every lane the best such match of its left neighbours where its own walk found less (the depth limit cuts walks
+        // short; in text the best match of p + 1 is usually the tail of the one at p).
+        // Measured and dropped (profiles/round2_notes.md): rounds of "walk until a candidate survives, then extend all survivors
+        // together" (the walks of a tile then run one after the other: 36.2 ms against 29.8 ms per 512 MiB of text), and
+        // inheriting after the first 1-4 candidates already, to raise the bar for the rest of the walk (+3 % on text, +10 % on
+        // the near-incompressible C2 files, where tiles without any match pay for the shuffles).
         for (;;) {
             uint32_t tile = 0;
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
@@ -296,29 +307,43 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
 
             const uint32_t p = tile * 32u + lane;
             uint32_t best_len = 2u, best_dist = 0u;
+            uint32_t maxlen = 0u;
             if (p < nhash) {
-                const uint32_t maxlen = (n - p) < ZWZ_MAX_MATCH ? (n - p) : ZWZ_MAX_MATCH;
+                maxlen = (n - p) < ZWZ_MAX_MATCH ? (n - p) : ZWZ_MAX_MATCH;
                 const uint32_t limit = p > ZWZ_MAX_DIST ? p - ZWZ_MAX_DIST : 0u;
                 const uint32_t span = p - limit;            // a candidate is usable iff 0 <= cand - limit < span (NIL fails)
-                const uint32_t ap = sD + p;                 // shared address of the scan position
-                const uint32_t first3 = lds32u(ap) & 0x00ffffffu;
-                uint32_t scan_end = lds8(ap + 2u), scan_end1 = lds8(ap + 1u); // bytes at best_len and best_len - 1
                 uint32_t cand = lds16(sP + 2u * p);
-                for (uint32_t budget = job.depth; budget != 0u && (cand - limit) < span; --budget) {
-                    const uint32_t ac = sD + cand;
-                    const uint32_t nxt = lds16(sP + 2u * cand); // next link is fetched while this candidate is examined
-                    // cheap rejects first (zlib's longest_match order): the byte that would extend the best match, its
-                    // predecessor, then the 3-byte prefix (hash collisions)
-                    if (lds8(ac + best_len) == scan_end) {
-                        if (lds8(ac + best_len - 1u) == scan_end1 && (lds32u(ac) & 0x00ffffffu) == first3) {
-                            uint32_t len = 3u;
-                            while (len < maxlen) {
-                                uint32_t y = lds32u(ac + len) ^ lds32u(ap + len);
-                                if (y) {
-                                    len += ((uint32_t) __ffs((int) y) - 1u) >> 3;
-                                    break;
+                if ((cand - limit) < span) {
+                    const uint32_t ap = sD + p;             // shared address of the scan position
+                    const uint32_t ka = ap & ~3u, sa = (ap & 3u) * 8u;
+                    const uint32_t a0 = lds32(ka), a1 = lds32(ka + 4u), a2 = lds32(ka + 8u), a3 = lds32(ka + 12u);
+                    const uint32_t S0 = __funnelshift_r(a0, a1, sa), S1 = __funnelshift_r(a1, a2, sa), S2 = __funnelshift_r(a2, a3, sa); // bytes [0, 12)
+                    uint32_t scan_end = (S0 >> 16) & 0xffu, scan_end1 = (S0 >> 8) & 0xffu; // bytes at best_len and best_len - 1
+                    for (uint32_t budget = job.depth; budget != 0u && (cand - limit) < span; --budget) {
+                        const uint32_t ac = sD + cand;
+                        const uint32_t nxt = lds16(sP + 2u * cand); // next link is fetched while this candidate is examined
+                        if (lds8(ac + best_len) == scan_end && lds8(ac + best_len - 1u) == scan_end1) {
+                            const uint32_t kc = ac & ~3u, sc = (ac & 3u) * 8u;
+                            const uint32_t c0 = lds32(kc), c1 = lds32(kc + 4u), c2 = lds32(kc + 8u), c3 = lds32(kc + 12u);
+                            const uint32_t x0 = __funnelshift_r(c0, c1, sc) ^ S0, x1 = __funnelshift_r(c1, c2, sc) ^ S1,
+                                           x2 = __funnelshift_r(c2, c3, sc) ^ S2;
+                            uint32_t len;
+                            if (x0) {
+                                len = ((uint32_t) __ffs((int) x0) - 1u) >> 3; // < 3: a hash collision
+                            } else if (x1) {
+                                len = 4u + (((uint32_t) __ffs((int) x1) - 1u) >> 3);
+                            } else if (x2) {
+                                len = 8u + (((uint32_t) __ffs((int) x2) - 1u) >> 3);
+                            } else {
+                                len = 12u;
+                                while (len < maxlen) {
+                                    uint32_t y = lds32u(ac + len) ^ lds32u(ap + len);
+                                    if (y) {
+                                        len += ((uint32_t) __ffs((int) y) - 1u) >> 3;
+                                        break;
+                                    }
+                                    len += 4u;
                                 }
-                                len += 4u;
                             }
                             if (len > maxlen) len = maxlen;
                             if (len > best_len) {
@@ -329,11 +354,26 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                                 scan_end1 = lds8(ap + len - 1u);
                             }
                         }
+                        cand = nxt;
                     }
-                    cand = nxt;
                 }
-                if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             }
+            if (__any_sync(ZWZ_FULL, best_len >= 4u)) { // inherit (a 3-byte match has no tail worth passing on)
+                uint32_t key = best_len >= 3u ? best_len + lane : 0u, kd = best_dist;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t ok = __shfl_up_sync(ZWZ_FULL, key, d), od = __shfl_up_sync(ZWZ_FULL, kd, d);
+                    if (lane >= (unsigned) d && ok > key) {
+                        key = ok;
+                        kd = od;
+                    }
+                }
+                if (key >= lane + 3u && key - lane > best_len && key - lane <= maxlen) { // maxlen = 0: no hash here (last two bytes)
+                    best_len = key - lane;
+                    best_dist = kd;
+                }
+            }
+            if (best_len == 3u && best_dist > 4096u) best_len = 2u; // zlib's TOO_FAR: such a match costs more than 3 literals
             // a tile without a single match is not written at all: the encoder takes its literals from the raw bytes
             const unsigned hit = __ballot_sync(ZWZ_FULL, best_len >= 3u);
             if (hit) {
@@ -352,19 +392,24 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         }
 
         // ---- 7. Adler-32 of the chunk ----
+        // Thread t takes the aligned words t, t + T, ... of the staging buffer (conflict-free; a contiguous byte range per
+        // thread put 32 lanes on two banks): a = sum of bytes, b = sum of (n - i) * byte_i, both by byte dot products.
         {
-            uint32_t seg = (n + T - 1u) / T;
-            uint32_t lo = tid * seg, hi = lo + seg;
-            if (lo > n) lo = n;
-            if (hi > n) hi = n;
             AdlerPart part;
             part.a = 0;
             part.b = 0;
-            part.len = hi - lo;
-            for (uint32_t i = lo; i < hi; ++i) { // seg <= 64: no overflow
-                part.a += datab[skew + i];
-                part.b += part.a;
+            part.len = 0; // b is kept position-weighted from the start: parts add up without length terms
+            const uint32_t nwords = (skew + n + 3u) >> 2;
+            for (uint32_t j = tid; j < nwords; j += T) { // <= 17 words per thread: (n - pos0) * 1020 * 17 < 2^32
+                uint32_t wv = dataw[j];
+                const int pos0 = (int) (4u * j) - (int) skew; // chunk position of the word's first byte
+                if (pos0 < 0) wv = pos0 <= -4 ? 0u : wv & (0xffffffffu << (8u * (uint32_t) (-pos0)));
+                if (pos0 + 4 > (int) n) wv &= 0xffffffffu >> (8u * (uint32_t) (pos0 + 4 - (int) n));
+                const uint32_t s4 = zwz_dp4a(wv, 0x01010101u), w4 = zwz_dp4a(wv, 0x03020100u);
+                part.a += s4;
+                part.b += (uint32_t) ((int) n - pos0) * s4 - w4;
             }
+            part.b %= 65521u;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 AdlerPart o;

@@ -28,6 +28,9 @@ namespace zwz {
 #define ZWZ_IF_R 96u                           // token entries (u16) a lane may emit per window
 #define ZWZ_IF_RS 98u                          // region stride in u16: 49 words (odd), so equal offsets in 32 regions hit 32 banks
 #define ZWZ_IF_MAXIT 6                         // rounds per window; then the proven prefix is committed and a new window starts
+#ifndef ZWZ_IF_MLP
+#define ZWZ_IF_MLP 4u                           // 32-byte rows of a resolve step whose back-reference loads are in flight together
+#endif
 #define ZWZ_IF_STG 1536u                       // output bytes assembled per resolve step (lives in the staged-window area)
 
 #ifdef ZWZ_EMU
@@ -237,29 +240,42 @@ ZWZ_DEV int inf_fast_block(SMEM &S, const BITS &B, uint64_t &bitpos, uint32_t ma
                 // matches that reach into this step's own output (source position + min(len, dist) > step start)
                 const unsigned deps = __ballot_sync(ZWZ_FULL, is_head && lane < take && excl + (olen < dn + 1u ? olen : dn + 1u) > dn + 1u);
                 // ---- every byte of the step by its own lane ----
-                for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
-                    const uint32_t b = b0 + lane;
-                    uint32_t j = 0;
+                // ZWZ_IF_MLP rows of 32 bytes at a time: the rows' back-reference loads (L2, ~600 cycles each) are all issued before
+                // the first value is stored, so a warp has ZWZ_IF_MLP loads in flight instead of one (long_scoreboard at the load
+                // was 26 % of all stall samples on text, profiles/round2_notes.md).
+                for (uint32_t b0 = 0; b0 < total; b0 += 32u * ZWZ_IF_MLP) {
+                    uint32_t val[ZWZ_IF_MLP];
+                    bool put[ZWZ_IF_MLP];
 #pragma unroll
-                    for (uint32_t sft = 16u; sft != 0u; sft >>= 1) {
-                        const uint32_t v = __shfl_sync(ZWZ_FULL, incl, (int) (j + sft - 1u));
-                        if (v <= b) j += sft;
-                    }
-                    j &= 31u; // lanes past `total` search past the end
-                    const uint32_t tj = __shfl_sync(ZWZ_FULL, t, (int) j);
-                    const uint32_t ej = __shfl_sync(ZWZ_FULL, excl, (int) j);
-                    const uint32_t dj = __shfl_sync(ZWZ_FULL, dn, (int) j) + 1u;
-                    if (b < total) {
-                        if ((hm >> j) & 1u) {
+                    for (uint32_t u = 0; u < ZWZ_IF_MLP; ++u) {
+                        const uint32_t b = b0 + 32u * u + lane;
+                        val[u] = 0;
+                        put[u] = false;
+                        if (b0 + 32u * u >= total) continue; // warp-uniform: a short step does not pay for empty rows
+                        uint32_t j = 0;
+#pragma unroll
+                        for (uint32_t sft = 16u; sft != 0u; sft >>= 1) {
+                            const uint32_t v = __shfl_sync(ZWZ_FULL, incl, (int) (j + sft - 1u));
+                            if (v <= b) j += sft;
+                        }
+                        j &= 31u; // lanes past `total` search past the end
+                        const uint32_t tj = __shfl_sync(ZWZ_FULL, t, (int) j);
+                        const uint32_t ej = __shfl_sync(ZWZ_FULL, excl, (int) j);
+                        const uint32_t dj = __shfl_sync(ZWZ_FULL, dn, (int) j) + 1u;
+                        val[u] = tj;
+                        put[u] = b < total;
+                        if (b < total && ((hm >> j) & 1u)) {
                             const uint32_t i = b - ej;                                                // byte i of the match
                             const uint32_t src = ej + (dj >= (tj & 0x1ffu) || i < dj ? i : i % dj);   // its source + dist, relative to the step
                             // before the step iff src < dj. No load for bytes that will not be written: those of a too-far match
                             // (dj > pos + ej) and those past the capacity of the output window (a sizing pass still counts them)
-                            if (src < dj && dj <= pos + ej && pos + b < cap) stg[b] = __ldcg(out + (pos + src - dj));
-                        } else {
-                            stg[b] = (uint8_t) tj;
+                            put[u] = src < dj && dj <= pos + ej && pos + b < cap;
+                            if (put[u]) val[u] = __ldcg(out + (pos + src - dj));
                         }
                     }
+#pragma unroll
+                    for (uint32_t u = 0; u < ZWZ_IF_MLP; ++u)
+                        if (put[u]) stg[b0 + 32u * u + lane] = (uint8_t) val[u];
                 }
                 __syncwarp();
                 // ---- matches that read this step's own output, in order (their sources lie in EARLIER tokens of the step) ----

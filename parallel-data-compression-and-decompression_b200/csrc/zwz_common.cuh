@@ -104,6 +104,17 @@ ZWZ_DEV uint32_t lds32u(uint32_t a) {
     return __funnelshift_r(lds32(k), lds32(k + 4u), (a & 3u) * 8u);
 }
 
+// sum over the four bytes of a of (byte of a) * (byte of b), unsigned
+#ifdef ZWZ_EMU
+ZWZ_DEV uint32_t zwz_dp4a(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r += ((a >> (8 * k)) & 0xffu) * ((b >> (8 * k)) & 0xffu);
+    return r;
+}
+#else
+ZWZ_DEV uint32_t zwz_dp4a(uint32_t a, uint32_t b) { return __dp4a(a, b, 0u); }
+#endif
+
 ZWZ_DEV uint32_t warp_incl_scan(uint32_t v) {
     unsigned l = lane_id();
 #pragma unroll

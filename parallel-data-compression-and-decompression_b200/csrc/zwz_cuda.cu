@@ -132,13 +132,19 @@ int fail(zwz_ctx *ctx, int code, const char *what) {
 
 int reserve(zwz_ctx *ctx, Arena &a, size_t bytes, bool pinned) {
     if (a.cap >= bytes && a.p) return ZWZ_OK;
+    const size_t old_cap = a.p ? a.cap : 0;
     if (a.p) {
         zwz_rt::stream_sync(ctx->stream);
         if (a.pinned) zwz_rt::free_pinned(a.p); else if (ctx->arena_async) zwz_rt::free_arena(a.p, ctx->stream); else zwz_rt::free_device(a.p);
         a.p = nullptr;
         a.cap = 0;
     }
-    size_t want = bytes + bytes / 4 + 4096; // grow-only, with headroom: batches of one job differ by a few percent
+    // grow-only, with headroom (batches of one job differ by a few percent) and geometric from the second time on: a job whose
+    // batches hold more and more, smaller and smaller files (the size-sorted deal) would otherwise re-allocate its descriptor
+    // arenas batch after batch — and a re-allocation waits for the device, i.e. for every other worker's kernels
+    // (profiles/round2_notes.md: 50-500 ms `reserve` phases in the end-to-end trace)
+    size_t want = bytes + bytes / 4 + 4096;
+    if (old_cap) want = std::max(want, std::min(old_cap * 2, bytes + ((size_t) 1 << 30)));
     int rc = pinned ? zwz_rt::malloc_pinned(&a.p, want) : (ctx->arena_async ? zwz_rt::malloc_arena(&a.p, want, ctx->stream) : zwz_rt::malloc_device(&a.p, want));
     if (rc) {
         a.p = nullptr;
@@ -212,13 +218,17 @@ struct Trace {
     }
 };
 
+#ifndef ZWZ_L0_DEPTH
+#define ZWZ_L0_DEPTH 12
+#define ZWZ_L0_NICE 48
+#endif
 struct LevelParams {
     uint32_t depth, nice;
 };
 LevelParams level_params(int level) {
     // search effort per level (hash-chain candidates per position, stop length). 0 = default: the cheapest setting that
     // stays inside the 3 % size tolerance on every corpus class (tests/test_kernels.py::test_deflate_ratio...)
-    static const LevelParams t[10] = {{16, 64}, {4, 16}, {6, 24}, {8, 32}, {16, 64}, {24, 96}, {32, 128}, {64, 160}, {128, 258}, {512, 258}};
+    static const LevelParams t[10] = {{ZWZ_L0_DEPTH, ZWZ_L0_NICE}, {4, 16}, {6, 24}, {8, 32}, {16, 64}, {24, 96}, {32, 128}, {64, 160}, {128, 258}, {512, 258}};
     if (level < 0 || level > 9) level = 0;
     return t[level];
 }

@@ -96,11 +96,19 @@ std::string md5_of_file_ctx(zwz_ctx *ctx, const std::string &file_path) {
         return "";
     }
     const size_t piece = (size_t) 64 << 20; // multiple of 64
-    void *pin = nullptr, *dev = nullptr;
-    if (zwz_malloc_pinned(ctx, piece, &pin) != ZWZ_OK || zwz_malloc_device(ctx, piece + 64, &dev) != ZWZ_OK) {
-        std::fclose(f);
+    struct Guard { // every exit — the throws below included — closes the file and returns both staging buffers
+        zwz_ctx *ctx;
+        FILE *f;
+        void *pin = nullptr, *dev = nullptr;
+        ~Guard() {
+            if (f) std::fclose(f);
+            if (pin) zwz_free_pinned(ctx, pin);
+            if (dev) zwz_free_device(ctx, dev);
+        }
+    } g{ctx, f};
+    if (zwz_malloc_pinned(ctx, piece, &g.pin) != ZWZ_OK || zwz_malloc_device(ctx, piece + 64, &g.dev) != ZWZ_OK)
         throw std::runtime_error(std::string("zwz: staging allocation failed: ") + zwz_last_error(ctx));
-    }
+    void *const pin = g.pin, *const dev = g.dev;
     uint32_t state[4];
     zwz_md5_state_init(state, 1);
     uint64_t total = 0;
@@ -124,9 +132,6 @@ std::string md5_of_file_ctx(zwz_ctx *ctx, const std::string &file_path) {
             done = true;
         }
     }
-    std::fclose(f);
-    zwz_free_pinned(ctx, pin);
-    zwz_free_device(ctx, dev);
     char hex[33];
     zwz_md5_hex(digest, hex);
     hex[32] = 0;
