@@ -632,6 +632,8 @@ def main():
     last_part = [None] * W
     hc_ptr, hr_ptr, hb_ptr = h_comp.data_ptr(), h_raw.data_ptr(), h_back.data_ptr()
     workers = [zwz_b200.Context(local_rank) for _ in range(W)]
+    for w in workers:   # like `main`'s workers: scratch for 64 MiB deflate passes instead of the default 4 GiB ones
+        w.tune(w.TUNE_DEFLATE_SUBBATCH_BYTES, 64 << 20)
     wlock = threading.Lock()
     wfree = list(range(W))
     comp_bytes = [0] * nparts
@@ -707,7 +709,10 @@ def main():
     prof = ctx.profile_read(True)
     ctx.profile_enable(False)
 
-    # e2e
+    # e2e (host buffers only: the device-resident copies of the shard are not needed any more — at 32 GB per GPU, C5 over two
+    # GPUs, they and the workers' arenas do not fit side by side)
+    del d_raw, d_slots, d_back, d_packed
+    torch.cuda.empty_cache()
     e2e_ms, e2e_launches = float("nan"), 0
     if not args.no_e2e:
         size_workers()

@@ -181,6 +181,12 @@ class Context:
 
     PROF_KINDS = ("lz_match", "deflate_encode", "inflate", "md5", "pack", "adler32")
 
+    TUNE_DEFLATE_SUBBATCH_BYTES = 1
+
+    def tune(self, what: int, value: int):
+        """zwz_ctx_tune: e.g. TUNE_DEFLATE_SUBBATCH_BYTES (raw bytes per internal deflate pass; the scratch is 6 bytes per raw byte of one pass)."""
+        self._check(self.lib.zwz_ctx_tune(self.h, what, value))
+
     def profile_enable(self, on: bool = True):
         self._check(self.lib.zwz_profile_enable(self.h, 1 if on else 0))
 

@@ -37,6 +37,24 @@
 namespace zwz {
 
 #define ZWZ_DM_NIL 0xffffu
+#ifndef ZWZ_DM_NOISE_BITS
+#define ZWZ_DM_NOISE_BITS 7.7f // order-0 entropy (bits per byte, over 1 024 bytes) above which a stretch is not searched
+#endif
+
+#ifdef ZWZ_EMU
+// test-only counters of the emulator build: [0] stretches left out as noise, [1] chunks whose noise candidates were kept because
+// they repeat, [2] chunks seen
+static uint64_t g_dm_stats[4];
+extern "C" void zwz_emu_match_stats(uint64_t *out, int reset) {
+    for (int i = 0; i < 4; ++i) {
+        out[i] = g_dm_stats[i];
+        if (reset) g_dm_stats[i] = 0;
+    }
+}
+#define ZWZ_DM_STAT(i, v) do { g_dm_stats[i] += (v); } while (0)
+#else
+#define ZWZ_DM_STAT(i, v) do { } while (0)
+#endif
 
 template <int CLS> struct MatchClass;
 template <> struct MatchClass<0> {
@@ -63,6 +81,8 @@ struct MatchCtl {
     uint32_t next_tile;
     uint32_t cur_work;
     uint32_t nmatch;           // positions of this chunk that found a match
+    uint32_t skip[2];          // bit k: the 1 024-byte stretch k looks like noise and is left out of the search
+    uint32_t coll;             // repeated 4-byte windows among the noise candidates
     uint32_t base[33];         // list k = entries [base[k], base[k+1]) of the position list
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
@@ -105,6 +125,8 @@ ZWZ_DEV void dm_mbar_wait(unsigned long long *bar, uint32_t parity) {
 }
 #endif
 
+ZWZ_DEV uint32_t sD_of(const unsigned char *smem, uint32_t skew) { return smem_addr(smem) + skew; }
+
 template <int CLS>
 ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJob job, const uint32_t *__restrict__ order, uint32_t n_work,
                                                                          uint32_t *work_counter) {
@@ -144,11 +166,12 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
 #else
         for (uint32_t i = tid; i < skew + n; i += T) smem[i] = i < skew ? 0 : src[i - skew];
 #endif
-        for (uint32_t i = tid; i < (1u << HB) / 2u; i += T) ((uint32_t *) head)[i] = 0xffffffffu;
         for (uint32_t i = tid; i < NW * NW / 2u; i += T) ((uint32_t *) cnt)[i] = 0u;
         if (tid == 0) {
             ctl->next_tile = 0;
             ctl->nmatch = 0;
+            ctl->skip[0] = 0;
+            ctl->skip[1] = 0;
         }
 #ifndef ZWZ_EMU
         if (stage_bytes) dm_mbar_wait(&ctl->mbar, parity);
@@ -158,6 +181,84 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         // bytes past the end take part in 4-byte compares: make them deterministic (the final clamp to `maxlen` makes
         // their value irrelevant for the result)
         if (tid < 32u) smem[skew + n + tid] = 0;
+
+        // ---- 1b. stretches of noise are left out ----
+        // A 1 024-byte stretch whose bytes are (nearly) uniformly distributed — the entropy-coded body of a JPEG, anything
+        // compressed or encrypted — holds no match worth a token, and everything below would be spent on proving that: its
+        // positions are neither hashed nor chained nor searched (LZ4 and zstd step over such data with a growing stride; here
+        // the decision is made per stretch, up front). Two tests, both in the (not yet initialised) head[] table:
+        //   (1) per stretch, one warp: byte histogram in the warp's 1 KB slice; order-0 entropy of 1 024 uniformly random bytes
+        //       is 7.82 +- 0.02 bits, of text ~4.5, of the structured binary classes of the corpus < 7: candidates lie above
+        //       ZWZ_DM_NOISE_BITS;
+        //   (2) over all candidates of the chunk: a flat histogram does not rule out repeats (a permutation table stored four
+        //       times, a random block stored twice), so every 4-byte window of the candidates is hashed into a bit set
+        //       (table size = 4-8 bits per position) and the windows that find their bit already set are counted. Noise of
+        //       n_c positions in m bits collides n_c^2 / 2m times; n_c / 16 more than that and NO stretch is left out.
+        // What this gives up: repeats that cover less than ~6 % of the noise (zlib would find them). The encoder emits these
+        // stretches as stored blocks (deflate_encode.cuh: quiet stretches).
+        {
+            uint32_t *hist = (uint32_t *) head + wid * 256u;
+            const uint32_t nfull = n >> 10; // the partial last stretch is always searched
+            for (uint32_t kb = wid; kb < nfull; kb += NW) {
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) hist[lane + 32u * j] = 0u;
+                __syncwarp();
+                const uint32_t w0 = (skew + (kb << 10)) >> 2; // aligned words: up to 3 bytes of the neighbour do not matter here
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    const uint32_t wv = dataw[w0 + lane + 32u * j];
+                    atomicAdd(&hist[wv & 0xffu], 1u);
+                    atomicAdd(&hist[(wv >> 8) & 0xffu], 1u);
+                    atomicAdd(&hist[(wv >> 16) & 0xffu], 1u);
+                    atomicAdd(&hist[wv >> 24], 1u);
+                }
+                __syncwarp();
+                float sum = 0.f; // sum of c * log2(c)
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    const float cf = (float) hist[lane + 32u * j];
+                    if (cf > 1.f) sum += cf * zwz_log2f(cf);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(ZWZ_FULL, sum, d);
+                // H = 10 - sum / 1024 > ZWZ_DM_NOISE_BITS
+                if (lane == 0 && sum < (10.f - ZWZ_DM_NOISE_BITS) * 1024.f) atomicOr(&ctl->skip[kb >> 5], 1u << (kb & 31u));
+                __syncwarp();
+            }
+            __syncthreads();
+            const uint64_t cand = (uint64_t) ctl->skip[0] | ((uint64_t) ctl->skip[1] << 32);
+            if (cand) { // CTA-uniform
+                constexpr uint32_t BB = HB + 4u; // head[] is 2 << HB bytes = 1 << BB bits
+                uint32_t *bits = (uint32_t *) head;
+                __syncthreads(); // the histograms are done with
+                for (uint32_t i = tid; i < (1u << BB) / 32u; i += T) bits[i] = 0u;
+                if (tid == 0) ctl->coll = 0;
+                __syncthreads();
+                uint32_t mine = 0;
+                for (uint32_t st = wid; st < nfull * 32u; st += NW) {
+                    if (!((cand >> (st >> 5)) & 1ull)) continue;
+                    const uint32_t h = (lds32u(sD_of(smem, skew) + st * 32u + lane) * 0x9E3779B1u) >> (32u - BB);
+                    const uint32_t old = atomicOr(&bits[h >> 5], 1u << (h & 31u));
+                    mine += (uint32_t) __popc(__ballot_sync(ZWZ_FULL, (old >> (h & 31u)) & 1u));
+                }
+                if (lane == 0 && mine) atomicAdd(&ctl->coll, mine);
+                __syncthreads();
+                const uint32_t nc = (uint32_t) __popcll((long long) cand) << 10;
+                const uint32_t allowed = (uint32_t) (((uint64_t) nc * nc) >> (BB + 1u)) + (nc >> 4);
+                if (tid == 0 && ctl->coll > allowed) {
+                    ctl->skip[0] = 0;
+                    ctl->skip[1] = 0;
+                    ZWZ_DM_STAT(1, 1);
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < (1u << HB) / 2u; i += T) ((uint32_t *) head)[i] = 0xffffffffu;
+        const uint64_t skipmask = (uint64_t) ctl->skip[0] | ((uint64_t) ctl->skip[1] << 32);
+        if (tid == 0) {
+            ZWZ_DM_STAT(0, (uint64_t) __popcll((long long) skipmask));
+            ZWZ_DM_STAT(2, 1);
+        }
         __syncthreads();
 
         uint32_t *mout = job.scratch + job.scr_off[c];
@@ -176,6 +277,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         // Same-range lanes of a step are found with LB ballots (a 5-bit match_any), so ranks inside a step follow lane
         // (= position) order and the lists come out sorted by position.
         for (uint32_t st = wid * spw; st < (wid + 1u) * spw && st < nsteps; ++st) {
+            if ((skipmask >> (st >> 5)) & 1ull) continue; // noise: not inserted
             const uint32_t p = st * 32u + lane;
             const bool valid = p < nhash;
             uint32_t h = 0;
@@ -212,6 +314,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         __syncthreads();
         // ---- 4. scatter positions into the lists (stable) ----
         for (uint32_t st = wid * spw; st < (wid + 1u) * spw && st < nsteps; ++st) {
+            if ((skipmask >> (st >> 5)) & 1ull) continue;
             const uint32_t p = st * 32u + lane;
             const bool valid = p < nhash;
             const uint32_t h = valid ? lds16(sP + 2u * p) : 0u;
@@ -304,6 +407,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
             tile = __shfl_sync(ZWZ_FULL, tile, 0);
             if (tile >= ntiles) break;
+            if ((skipmask >> (tile >> 5)) & 1ull) continue; // noise: not searched, not written (the encoder reads the raw bytes)
 
             const uint32_t p = tile * 32u + lane;
             uint32_t best_len = 2u, best_dist = 0u;

@@ -412,6 +412,32 @@ def test_deflate_stored_regions_inside_a_chunk(ctx, is_gpu):
     assert ours <= zl, (ours, zl)   # a stored stretch costs 5 bytes; zlib pays 8-bit-plus literals for it
 
 
+def test_deflate_noise_stretches_and_repeats_inside_them(ctx, is_gpu):
+    """The match kernel leaves 1 024-byte stretches of noise out of its search (flat byte histogram AND no more repeated 4-byte
+    windows than chance gives). Data with a flat histogram that DOES repeat must still be found: a permutation table stored
+    several times, a random block stored twice (criterion (4): size within tolerance of zlib's)."""
+    rnd = corpus.gen_random(70000, 596, 91).tobytes()
+    text = corpus.gen_text(20000, 596, 92).tobytes()
+    perm = bytes(np.random.Generator(np.random.Philox(key=[596, 93])).permutation(256).astype(np.uint8))
+    chunks = [bytes(range(256)) * 16, perm * 40, rnd[:3000] + rnd[:3000], rnd[:9000] + rnd[2000:9000] + rnd[:5000],
+              rnd[:20000], text[:5000] + rnd[:12000] + text[:5000], rnd[:6000] + text[:3000] + rnd[30000:36000], rnd[:CHUNK],
+              (rnd[:4096] + text[:1000]) * 9]
+    stats = None
+    if not is_gpu:   # the emulator build counts what the kernel decided
+        import ctypes
+        stats = (ctypes.c_uint64 * 4)()
+        ctx.lib.zwz_emu_match_stats(stats, 1)
+    sizes, res = _deflate_and_verify(ctx, chunks)
+    for c, s in zip(chunks, sizes):
+        assert s <= len(zlib.compress(c, 6)) * RATIO_TOLERANCE + 16, (len(c), s, len(zlib.compress(c, 6)))
+    if stats is not None:
+        ctx.lib.zwz_emu_match_stats(stats, 1)
+        left_out, kept_for_repeats, seen = int(stats[0]), int(stats[1]), int(stats[2])
+        assert seen == len(chunks)
+        assert kept_for_repeats == 5          # the two tables, the two repeated random blocks, and the (noise + text) x 9 chunk
+        assert left_out >= 19 + 10 + 4 + 4 + 63   # full stretches of pure noise in chunks 4..7 (stretches that straddle a boundary may go either way)
+
+
 def test_deflate_length_limited_codes(ctx):
     """Fibonacci-like symbol frequencies push the unrestricted Huffman depth past 15 bits (and the code-length code past
     7): the length-limiting repair has to leave a complete, decodable code."""

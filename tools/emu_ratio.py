@@ -16,6 +16,9 @@ classes = {
     "c3log":  [corpus.c3_buffer(CH * 6, 596)[i * CH:(i + 1) * CH].tobytes() for i in range(6)],
     "small":  [corpus.gen_text(3000 + 700 * i, 596, 230 + i).tobytes() for i in range(12)] + [corpus.gen_struct(5000 + 900 * i, 596, 250 + i).tobytes() for i in range(8)],
 }
+_b, _o, _ = corpus.c2_buffer(150, 596)
+classes["c2"] = [_b[int(_o[i]):int(_o[i + 1])].tobytes() for i in range(150)]
+classes["jpeg"] = [corpus.gen_jpeg_like(3000 + 1777 * i, 596, 300 + i).tobytes() for i in range(12)]
 tot_o = tot_z = 0
 for name, chunks in classes.items():
     raw = b"".join(chunks)
