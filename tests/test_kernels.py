@@ -409,7 +409,9 @@ def test_deflate_stored_regions_inside_a_chunk(ctx, is_gpu):
         assert st == O.STREAM_END and back == c, i
         ours += len(p)
         zl += len(zlib.compress(c, 6))
-    assert ours <= zl, (ours, zl)   # a stored stretch costs 5 bytes; zlib pays 8-bit-plus literals for it
+    # a stored stretch costs 5 bytes where zlib pays 8-bit-plus literals; the lone matches planted INSIDE the noise are not looked
+    # for any more (deflate_match.cuh: noise stretches) — the two about cancel on this set; the bar is the tolerance of criterion (4)
+    assert ours <= zl * 1.003, (ours, zl)
 
 
 def test_deflate_noise_stretches_and_repeats_inside_them(ctx, is_gpu):
