@@ -10,7 +10,7 @@ timeout 900 $TR bench.py --gpus $N --workload c5 --steps 2 --no-cpu-baseline > $
 python - $O/bench_c5.json <<'PY'
 import json,sys
 try:
-    d=json.load(open(sys.argv[1])); print("c5", d["n_gpus"], "value", round(d["value"],2), "e2e", round(d["e2e"]["value"],2), {k:round(v,1) for k,v in d["kernel_ms_per_step"].items()}, d["config"]["workload"][:80])
+    d=[json.loads(l) for l in open(sys.argv[1]) if l.startswith("{")][-1]; print("c5", d["n_gpus"], "value", round(d["value"],2), "e2e", round(d["e2e"]["value"],2), {k:round(v,1) for k,v in d["kernel_ms_per_step"].items()}, d["config"]["workload"][:80])
 except Exception as e: print("c5 ERR", e)
 PY
 tail -3 $O/bench_c5.err
@@ -20,7 +20,7 @@ if [ "$2" = "full" ]; then
   python - $O/bench_c2.json <<'PY'
 import json,sys
 try:
-    d=json.load(open(sys.argv[1])); print("c2", d["n_gpus"], "value", round(d["value"],2), "e2e", round(d["e2e"]["value"],2))
+    d=[json.loads(l) for l in open(sys.argv[1]) if l.startswith("{")][-1]; print("c2", d["n_gpus"], "value", round(d["value"],2), "e2e", round(d["e2e"]["value"],2))
 except Exception as e: print("c2 ERR", e)
 PY
   # CLI on N GPUs: C1-shaped 2 GB tree, then ONE 2 GiB text file cut over the N GPUs (the reference reads both back)
