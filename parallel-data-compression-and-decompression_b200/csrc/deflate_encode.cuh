@@ -312,7 +312,8 @@ ZWZ_DEV_NOINLINE uint32_t enc_stored_stream(uint8_t *out, const uint8_t *src, ui
         out[9 + n] = (uint8_t) (adler >> 8);
         out[10 + n] = (uint8_t) adler;
     }
-    for (uint32_t i = lane; i < n; i += 32u) out[7u + i] = src[i];
+    __syncwarp();
+    inf_copy_plain(out + 7u, src, n);
     return n + 11u;
 }
 
@@ -640,17 +641,28 @@ ZWZ_DEV_NOINLINE void enc_emit_stored_block(BitSink *kp, const uint8_t *src, uin
         nb = 32u;
     }
     sink_put(S, k, v, nb);
-    for (uint32_t base = 0; base < nbytes; base += 128u) {
-        const uint32_t i = base + 4u * lane;
-        uint32_t w = 0, cnt = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j)
-            if (i + j < nbytes) {
-                w |= (uint32_t) src[i + j] << (8u * j);
-                ++cnt;
-            }
-        sink_put(S, k, (uint64_t) w, 8u * cnt);
-    }
+    // The stream is at a byte boundary now and the payload is plain bytes: they go straight to the slot (16-byte stores) instead
+    // of through the bit sink, which is then set up again behind them. Bytes the sink still holds (< 4) are written out first.
+    uint8_t *ob = (uint8_t *) k.outw;
+    const uint32_t cap_bytes = k.cap_words * 4u;
+    const uint32_t pend = k.fill >> 3, b0 = k.nwords * 4u;
+    const uint32_t held = S.stage[0];
+    __syncwarp();
+    if (lane < pend && b0 + lane < cap_bytes) ob[b0 + lane] = (uint8_t) (held >> (8u * lane));
+    const uint32_t dst = b0 + pend, end = dst + nbytes; // nbytes >= ZWZ_DE_STORED_MIN: the last word's bytes all come from src
+    const uint32_t ncopy = dst >= cap_bytes ? 0u : (end <= cap_bytes ? nbytes : cap_bytes - dst); // past the slot the sink only counts
+    __syncwarp();
+    if (ncopy) inf_copy_plain(ob + dst, src, ncopy);
+    const uint32_t tail = end & 3u;
+    uint32_t tw = 0;
+    if (lane == 0)
+        for (uint32_t j = 0; j < tail; ++j) tw |= (uint32_t) src[nbytes - tail + j] << (8u * j);
+    __syncwarp();
+    S.stage[lane] = lane == 0 ? tw : 0u;
+    S.stage[lane + 32u] = 0u;
+    __syncwarp();
+    k.nwords = end >> 2;
+    k.fill = tail * 8u;
     *kp = k;
 }
 
@@ -772,6 +784,19 @@ ZWZ_DEV void enc_chunk(EncWarpSmem &S, const DeflateJob &job, uint32_t c) {
         // the window after this one, fetched before it is known to be needed: when the window holds no match that leaves
         // it (J0 == 32: every literal-only stretch) the next step starts without waiting on a dependent load
         const uint32_t mnx = ENC_WORD_AT(q + 32u);
+        // quiet step: no tile under [p, p + 32) holds a match, so all 32 positions are literals and the path through them needs
+        // no pointer doubling (the bodies of JPEG-like files, noise in general: 70 % of the steps of config C2)
+        {
+            const uint32_t ta = p >> 5, tb = (p + 31u) >> 5;
+            if (p + 32u <= n && !(((S.tflags[ta >> 5] >> (ta & 31u)) | (S.tflags[tb >> 5] >> (tb & 31u))) & 1u)) {
+                atomicAdd(&S.freq[m0 >> 24], 1u);
+                m[ntok + lane] = m0 & 0xff000000u;
+                ntok += 32u;
+                p += 32u;
+                m0 = mnx;
+                continue;
+            }
+        }
         uint32_t m1 = __shfl_down_sync(ZWZ_FULL, m0, 1);
         const uint32_t mfirst = __shfl_sync(ZWZ_FULL, mnx, 0);
         if (lane == 31u) m1 = mfirst;

@@ -168,6 +168,35 @@ ZWZ_DEV uint32_t scr_match_words(uint32_t n) { return (n + 2u + 31u) & ~31u; }
 ZWZ_DEV uint32_t scr_list_words(uint32_t n) { return ((n + 1u) / 2u + 32u + 31u) & ~31u; }
 ZWZ_DEV uint32_t scr_flag_offset(uint32_t n) { return scr_match_words(n) + scr_list_words(n); }
 
+// ---- vectorised plain copy (stored blocks): out[0..n) = src[0..n), any alignment of either side ----
+// 16-byte stores to the aligned middle of the destination; the source words come from aligned 32-bit loads shifted into
+// place, so nothing outside the aligned words that hold src[0..n) is read.
+ZWZ_DEV void inf_copy_plain(uint8_t *dst, const uint8_t *src, uint32_t n) {
+    const unsigned lane = lane_id();
+    uint32_t head = (16u - (uint32_t) ((uintptr_t) dst & 15u)) & 15u;
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t nvec = (n - head) >> 4;
+    const uint8_t *s = src + head;
+    uint8_t *d = dst + head;
+    const uint32_t a = (uint32_t) ((uintptr_t) s & 3u);
+    const uint32_t *sw = (const uint32_t *) (s - a);
+    const uint32_t sh = a * 8u;
+    for (uint32_t v = lane; v < nvec; v += 32u) {
+        const uint32_t *w = sw + 4u * v;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        const uint32_t w4 = a ? __ldg(w + 4) : 0u; // a == 0: the fifth word is not part of the source
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, sh);
+        o.y = __funnelshift_r(w1, w2, sh);
+        o.z = __funnelshift_r(w2, w3, sh);
+        o.w = __funnelshift_r(w3, w4, sh);
+        *(uint4 *) (d + 16u * v) = o;
+    }
+    const uint32_t done = head + (nvec << 4);
+    if (done + lane < n) dst[done + lane] = src[done + lane]; // tail < 16 bytes
+}
+
 // ---- DEFLATE symbol arithmetic (RFC 1951 §3.2.5) without tables ----------------------------------------------------
 // length 3..258 -> (symbol 257..285, extra bit count, extra value)
 ZWZ_DEV void len_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
