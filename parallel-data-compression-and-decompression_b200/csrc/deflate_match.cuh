@@ -414,7 +414,10 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
             if (lane == 0) tile = atomicAdd(&ctl->next_tile, 1u);
             tile = __shfl_sync(ZWZ_FULL, tile, 0);
             if (tile >= ntiles) break;
-            if ((skipmask >> (tile >> 5)) & 1ull) continue; // noise: not searched, not written (the encoder reads the raw bytes)
+            if ((skipmask >> (tile >> 5)) & 1ull) { // noise: not searched, not written (the encoder reads the raw bytes)
+                if (lane == 0) atomicMax(&ctl->next_tile, ((tile >> 5) + 1u) << 5); // the rest of the stretch need not be handed out tile by tile
+                continue;
+            }
 
             const uint32_t p = tile * 32u + lane;
             uint32_t best_len = 2u, best_dist = 0u;
