@@ -3,6 +3,7 @@
 // The deal itself (rank r takes sorted files r, r+P, ...; compression.cpp:31-41) is the multi-GPU sharding rule of this
 // build: GPU index in place of MPI rank, no payload ever crosses GPUs.
 #include "zwz_host.hpp"
+#include <unistd.h>
 
 #include <algorithm>
 #include <cctype>
@@ -131,10 +132,16 @@ std::vector<FileEntry> collect_and_sort(const fs::path &path) {
 std::string sort_files_by_size(const fs::path &path) {
     std::vector<FileEntry> files = collect_and_sort(path);
     auto output_filename = path.parent_path() / "sorted_files_by_size.txt"; // file_sort.cpp:33
-    std::ofstream file(output_filename);
-    if (file.is_open()) {
-        for (const auto &e : files) file << e.relpath << "\n";
+    // written beside its place and renamed into it: a rank that opens the record file sees all of it or the previous one, never
+    // half of it
+    const std::string tmp = output_filename.string() + ".tmp" + std::to_string((long) getpid());
+    {
+        std::ofstream file(tmp);
+        if (file.is_open()) {
+            for (const auto &e : files) file << e.relpath << "\n";
+        }
     }
+    if (std::rename(tmp.c_str(), output_filename.c_str()) != 0) std::remove(tmp.c_str());
     return output_filename.string();
 }
 

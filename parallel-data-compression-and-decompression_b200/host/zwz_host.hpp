@@ -68,6 +68,10 @@ RunStats &stats();
 
 // C entry points for ctypes / other FFIs (same semantics as the C++ functions above)
 extern "C" {
+// NOT re-entrant: these entry points set the process-wide run configuration and statistics (one run per process at a time, like
+// the reference's `main`). zwz_host_compress with world_rank != 0 reads <input_dir>/../sorted_files_by_size.txt: the caller runs
+// rank 0's zwz_host_sort_files_by_size (or its whole zwz_host_compress) first — the record file is published by rename, so a
+// reader never sees half of it, but only the caller can know that it is THIS run's.
 int zwz_host_compress(const char *input_dir, const char *output_dir, int world_rank, int world_size, int device, int level);
 int zwz_host_decompress(const char *input_dir, const char *output_dir, int device);
 int zwz_host_md5_of_file(const char *path, int device, char hex_out[33]);
