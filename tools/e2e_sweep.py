@@ -39,7 +39,7 @@ for W, P in settings:
     desc = bench.part_descriptors(sh, coff, clen, cfile, raw_off, slot_off, part_chunk, part_file, None)
     workers = [zwz_b200.Context(0, library=LIB) if EMU else zwz_b200.Context(0) for _ in range(W)]
     for w in workers:
-        w.tune(w.TUNE_DEFLATE_SUBBATCH_BYTES, 64 << 20)
+        w.tune(w.TUNE_DEFLATE_SUBBATCH_BYTES, int(os.environ.get("ZWZ_SWEEP_SUBBATCH_MB", "64")) << 20)
     lock = threading.Lock(); free = list(range(W))
 
     def run_part(i, wi):
