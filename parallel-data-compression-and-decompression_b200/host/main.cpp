@@ -227,7 +227,7 @@ int main(int argc, char *argv[]) {
     // One process drives one GPU: hide the others from the CUDA runtime before its first call. Without a persistence daemon
     // cuInit brings up EVERY visible device — measured on an 8-GPU box: 10-11.7 s of "init" per rank with 8 devices visible,
     // against ~1.2 s for one (profiles/round2/multi/).
-    if (compressing || decompressing) {
+    if ((compressing || decompressing) && !std::getenv("ZWZ_KEEP_DEVICES_VISIBLE")) { // the switch exists for A/B timing of exactly this
         cfg.box_gpus = visible_gpu_count();
         std::string one = std::to_string(cfg.device);
         if (const char *v = std::getenv("CUDA_VISIBLE_DEVICES")) { // entry number cfg.device of the list we were given
