@@ -224,32 +224,9 @@ int main(int argc, char *argv[]) {
         kids = fork_ranks(self_gpus);
     }
 
-    // One process drives one GPU: hide the others from the CUDA runtime before its first call. Without a persistence daemon
-    // cuInit brings up EVERY visible device — measured on an 8-GPU box: 10-11.7 s of "init" per rank with 8 devices visible,
-    // against ~1.2 s for one (profiles/round2/multi/).
-    if ((compressing || decompressing) && !std::getenv("ZWZ_KEEP_DEVICES_VISIBLE")) { // the switch exists for A/B timing of exactly this
-        cfg.box_gpus = visible_gpu_count();
-        std::string one = std::to_string(cfg.device);
-        if (const char *v = std::getenv("CUDA_VISIBLE_DEVICES")) { // entry number cfg.device of the list we were given
-            std::string list = v;
-            size_t b = 0;
-            for (int k = 0; k < cfg.device && b != std::string::npos; ++k) {
-                b = list.find(',', b);
-                if (b != std::string::npos) ++b;
-            }
-            if (b != std::string::npos) {
-                const size_t e = list.find(',', b);
-                one = list.substr(b, e == std::string::npos ? std::string::npos : e - b);
-            }
-        }
-        if (!one.empty()) {
-            setenv("CUDA_VISIBLE_DEVICES", one.c_str(), 1);
-            cfg.device = 0;
-        }
-    }
-
-    // the CUDA runtime and this rank's first context come up (0.6–2.5 s on a fresh box) while the host walks and sorts the tree
-    // or maps and indexes the archives
+    // the CUDA runtime and this rank's first context come up (0.6–2.5 s on a fresh 1-GPU box, ~10 s per rank on the 8-GPU box —
+    // whether or not the other seven devices are hidden from the process: measured, profiles/round2/multi/n8_bringup_*.log) while
+    // the host walks and sorts the tree or maps and indexes the archives
     std::thread warm;
     if (compressing || decompressing) warm = std::thread([] { zwzhost::warm_device(); });
 

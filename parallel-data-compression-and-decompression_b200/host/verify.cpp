@@ -70,7 +70,7 @@ int worker_count() {
         // every worker is a host thread that reads, serialises and writes besides driving its CUDA stream: half the cores this
         // rank may use (the ranks of one box share them), at least 3
         int cores = (int) std::thread::hardware_concurrency();
-        int local_ranks = std::max(1, std::min(config().world_size, std::max(1, config().box_gpus > 0 ? config().box_gpus : visible_gpu_count())));
+        int local_ranks = std::max(1, std::min(config().world_size, std::max(1, visible_gpu_count())));
         // measured on a 16-core box (profiles/round2/cli): 3 and 4 workers tie, 8 lose a second or more — every worker brings
         // its own page-locked buffers and device arenas, and allocating those is the larger part of a 2 GB job
         w = std::max(2, std::min(4, cores / local_ranks / 4));

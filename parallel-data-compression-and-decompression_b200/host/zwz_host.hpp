@@ -43,8 +43,6 @@ struct RunConfig {
     bool quarantine = false;  // ZWZ_QUARANTINE=1: move files whose MD5 does not match to <output dir>/bad/ (README.md:175,186 promises
                               // it; the reference's code leaves them in place, and so does the default)
     std::size_t batch_bytes = (std::size_t) 128 << 20; // per worker (ZWZ_BATCH_MB)
-    int box_gpus = 0;         // GPUs of this box as seen BEFORE the process was pinned to one of them (0 = not pinned): the ranks
-                              // of a run share the box's cores, and the worker count follows from that
 };
 RunConfig &config();
 void config_from_env();

@@ -9,12 +9,12 @@ sys.path.insert(0, ".")
 from tools import corpus
 specs, tot = [], 0
 for s in corpus.c1_specs(1000, corpus.BASE_SEED):
-    if tot >= 400e6: break
+    if tot >= 300e6: break
     specs.append(s); tot += s.size
 corpus.write_tree("/dev/shm/t_c1/w/src", specs)
 PY
 M=parallel-data-compression-and-decompression_b200/host/main
-for mode in pinned visible pinned visible; do
+for mode in ${MODES:-pinned visible pinned visible}; do
   rm -rf /dev/shm/t_c1/arch /dev/shm/t_c1/out
   if [ $mode = visible ]; then export ZWZ_KEEP_DEVICES_VISIBLE=1; else unset ZWZ_KEEP_DEVICES_VISIBLE; fi
   ( time ZWZ_GPUS=$N ZWZ_TIMING=1 $M compress /dev/shm/t_c1/w/src /dev/shm/t_c1/arch ) > $O/c_$mode.log 2>&1
