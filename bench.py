@@ -822,7 +822,7 @@ def main():
             except Exception as e:  # the headline line must not die on an extra
                 extra["error"] = repr(e)
             line["extra_workloads"] = extra
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg is a rank-0, N = 1 item (at N > 1 the other ranks would wait for it)
             target = int(args.cpu_sample_mb * 1e6) if args.cpu_sample_mb else int(min(8e6 * cores, 400e6))
             sb, so, what = sample_of(sh, target)
             scoff, sclen, _, _ = corpus.chunk_table(so)
