@@ -58,20 +58,20 @@ extern "C" void zwz_emu_match_stats(uint64_t *out, int reset) {
 
 template <int CLS> struct MatchClass;
 template <> struct MatchClass<0> {
-    static constexpr uint32_t kCap = 8192, kThreads = 256, kHBits = 12, kData = 8192 + 64, kListBits = 3;
+    static constexpr uint32_t kCap = 8192, kThreads = 256, kHBits = 12, kData = 8192 + 64, kListBits = 3, kCtasPerSm = 6;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 8u * 8u;
 };
 template <> struct MatchClass<1> {
-    static constexpr uint32_t kCap = 16384, kThreads = 512, kHBits = 13, kData = 16384 + 64, kListBits = 4;
+    static constexpr uint32_t kCap = 16384, kThreads = 512, kHBits = 13, kData = 16384 + 64, kListBits = 4, kCtasPerSm = 3;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<2> {
     // 31 744, not 32 768: 2 x (smem + 1 KB) must fit the SM's 228 KB for two resident CTAs (115 712 B each at most)
-    static constexpr uint32_t kCap = 31744, kThreads = 512, kHBits = 13, kData = 31744 + 64, kListBits = 4;
+    static constexpr uint32_t kCap = 31744, kThreads = 512, kHBits = 13, kData = 31744 + 64, kListBits = 4, kCtasPerSm = 2;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 1024u + 2u * 16u * 16u;
 };
 template <> struct MatchClass<3> {
-    static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600, kListBits = 5;
+    static constexpr uint32_t kCap = 65535, kThreads = 1024, kHBits = 14, kData = 65600, kListBits = 5, kCtasPerSm = 1;
     static constexpr uint32_t kPrevBytes = ((kCap + 31u) & ~31u) * 2u, kSmem = kData + kPrevBytes + (2u << kHBits) + 640u + 2u * 32u * 32u;
 };
 
@@ -83,10 +83,14 @@ struct MatchCtl {
     uint32_t nmatch;           // positions of this chunk that found a match
     uint32_t skip[2];          // bit k: the 1 024-byte stretch k looks like noise and is left out of the search
     uint32_t coll;             // repeated 4-byte windows among the noise candidates
+    uint32_t coll2;            // candidate windows that also occur (by hash) among the other positions
     uint32_t base[33];         // list k = entries [base[k], base[k+1]) of the position list
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
 static_assert(sizeof(MatchCtl) <= 640, "MatchCtl must fit its slot");
+static_assert(MatchClass<0>::kPrevBytes >= (2u << MatchClass<0>::kHBits) && MatchClass<1>::kPrevBytes >= (2u << MatchClass<1>::kHBits) &&
+                  MatchClass<2>::kPrevBytes >= (2u << MatchClass<2>::kHBits) && MatchClass<3>::kPrevBytes >= (2u << MatchClass<3>::kHBits),
+              "the second bit set of the noise test lives in prev[]");
 static_assert(2u * (MatchClass<2>::kSmem + 1024u) <= 228u * 1024u && 3u * (MatchClass<1>::kSmem + 1024u) <= 228u * 1024u &&
                   6u * (MatchClass<0>::kSmem + 1024u) <= 228u * 1024u,
               "resident CTAs per SM assumed by the launch grids");
@@ -128,7 +132,7 @@ ZWZ_DEV void dm_mbar_wait(unsigned long long *bar, uint32_t parity) {
 ZWZ_DEV uint32_t sD_of(const unsigned char *smem, uint32_t skew) { return smem_addr(smem) + skew; }
 
 template <int CLS>
-ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJob job, const uint32_t *__restrict__ order, uint32_t n_work,
+ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads, MatchClass<CLS>::kCtasPerSm) lz_match_kernel(DeflateJob job, const uint32_t *__restrict__ order, uint32_t n_work,
                                                                          uint32_t *work_counter) {
     constexpr uint32_t T = MatchClass<CLS>::kThreads, HB = MatchClass<CLS>::kHBits, DATA = MatchClass<CLS>::kData;
     constexpr uint32_t NW = T / 32u, LB = MatchClass<CLS>::kListBits;
@@ -193,8 +197,9 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
         //   (2) over all candidates of the chunk: a flat histogram does not rule out repeats (a permutation table stored four
         //       times, a random block stored twice), so every 4-byte window of the candidates is hashed into a bit set
         //       (table size = 4-8 bits per position) and the windows that find their bit already set are counted. Noise of
-        //       n_c positions in m bits collides n_c^2 / 2m times; n_c / 16 more than that and NO stretch is left out.
-        // What this gives up: repeats that cover less than ~6 % of the noise (zlib would find them). The encoder emits these
+        //       n_c positions in m bits collides n_c^2 / 2m times (+- its square root); n_c / 64 + 48 more than that and NO
+        //       stretch is left out. The candidates' windows are also looked up among the windows of all other positions (below).
+        // What this gives up: repeats that cover less than ~2 % of the noise (zlib would find them). The encoder emits these
         // stretches as stored blocks (deflate_encode.cuh: quiet stretches).
         {
             uint32_t *hist = (uint32_t *) head + wid * 256u;
@@ -238,8 +243,15 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 constexpr uint32_t BB = HB + 4u; // head[] is 2 << HB bytes = 1 << BB bits
                 uint32_t *bits = (uint32_t *) head;
                 __syncthreads(); // the histograms are done with
-                for (uint32_t i = tid; i < (1u << BB) / 32u; i += T) bits[i] = 0u;
-                if (tid == 0) ctl->coll = 0;
+                uint32_t *bits2 = (uint32_t *) prev; // >= as large as head[] in every class
+                for (uint32_t i = tid; i < (1u << BB) / 32u; i += T) {
+                    bits[i] = 0u;
+                    bits2[i] = 0u;
+                }
+                if (tid == 0) {
+                    ctl->coll = 0;
+                    ctl->coll2 = 0;
+                }
                 __syncthreads();
                 uint32_t mine = 0;
                 for (uint32_t st = wid; st < nfull * 32u; st += NW) {
@@ -250,9 +262,32 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads) lz_match_kernel(DeflateJ
                 }
                 if (lane == 0 && mine) atomicAdd(&ctl->coll, mine);
                 __syncthreads();
+                // ... and against the OTHER positions: the copy of PART of a noise stretch need not be a candidate itself (its
+                // histogram is narrower), and bytes that are not inserted cannot be found by anyone. The other positions' windows
+                // set a second bit set (in the prev[] area, unused so far), the candidates' windows are looked up in it: noise
+                // windows are all different, so the hits are independent — n_c * n_other / m of them by chance at most (the
+                // other way round, text windows looked up in the noise set, one unlucky window repeats its hit a hundred times).
+                const uint32_t nh = n >= 3u ? n - 2u : 0u;
+                for (uint32_t st = wid; st * 32u < nh; st += NW) {
+                    if (st < nfull * 32u && ((cand >> (st >> 5)) & 1ull)) continue;
+                    const uint32_t q = st * 32u + lane;
+                    const uint32_t h = (lds32u(sD_of(smem, skew) + q) * 0x9E3779B1u) >> (32u - BB);
+                    if (q < nh) atomicOr(&bits2[h >> 5], 1u << (h & 31u));
+                }
+                __syncthreads();
+                uint32_t hits = 0;
+                for (uint32_t st = wid; st < nfull * 32u; st += NW) {
+                    if (!((cand >> (st >> 5)) & 1ull)) continue;
+                    const uint32_t h = (lds32u(sD_of(smem, skew) + st * 32u + lane) * 0x9E3779B1u) >> (32u - BB);
+                    hits += (uint32_t) __popc(__ballot_sync(ZWZ_FULL, (bits2[h >> 5] >> (h & 31u)) & 1u));
+                }
+                if (lane == 0 && hits) atomicAdd(&ctl->coll2, hits);
+                __syncthreads();
                 const uint32_t nc = (uint32_t) __popcll((long long) cand) << 10;
-                const uint32_t allowed = (uint32_t) (((uint64_t) nc * nc) >> (BB + 1u)) + (nc >> 4);
-                if (tid == 0 && ctl->coll > allowed) {
+                const uint32_t nother = nh > nc ? nh - nc : 0u;
+                const uint32_t allowed = (uint32_t) (((uint64_t) nc * nc) >> (BB + 1u)) + (nc >> 6) + 48u;
+                const uint32_t allowed2 = (uint32_t) (((uint64_t) nother * nc) >> BB) + (nc >> 6) + 48u;
+                if (tid == 0 && (ctl->coll > allowed || ctl->coll2 > allowed2)) {
                     ctl->skip[0] = 0;
                     ctl->skip[1] = 0;
                     ZWZ_DM_STAT(1, 1);
