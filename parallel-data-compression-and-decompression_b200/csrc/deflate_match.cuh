@@ -84,6 +84,7 @@ struct MatchCtl {
     uint32_t skip[2];          // bit k: the 1 024-byte stretch k looks like noise and is left out of the search
     uint32_t coll;             // repeated 4-byte windows among the noise candidates
     uint32_t coll2;            // candidate windows that also occur (by hash) among the other positions
+    uint32_t set2;             // bits set in the other positions' bit set
     uint32_t base[33];         // list k = entries [base[k], base[k+1]) of the position list
     uint32_t adler_a[32], adler_b[32], adler_len[32];
 };
@@ -251,6 +252,7 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads, MatchClass<CLS>::kCtasPe
                 if (tid == 0) {
                     ctl->coll = 0;
                     ctl->coll2 = 0;
+                    ctl->set2 = 0;
                 }
                 __syncthreads();
                 uint32_t mine = 0;
@@ -265,15 +267,18 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads, MatchClass<CLS>::kCtasPe
                 // ... and against the OTHER positions: the copy of PART of a noise stretch need not be a candidate itself (its
                 // histogram is narrower), and bytes that are not inserted cannot be found by anyone. The other positions' windows
                 // set a second bit set (in the prev[] area, unused so far), the candidates' windows are looked up in it: noise
-                // windows are all different, so the hits are independent — n_c * n_other / m of them by chance at most (the
+                // windows are all different, so the hits are independent — n_c * (bits set) / m of them by chance (the
                 // other way round, text windows looked up in the noise set, one unlucky window repeats its hit a hundred times).
                 const uint32_t nh = n >= 3u ? n - 2u : 0u;
+                uint32_t fresh = 0; // bits this warp was the first to set: the set's load decides what chance looks like
                 for (uint32_t st = wid; st * 32u < nh; st += NW) {
                     if (st < nfull * 32u && ((cand >> (st >> 5)) & 1ull)) continue;
                     const uint32_t q = st * 32u + lane;
                     const uint32_t h = (lds32u(sD_of(smem, skew) + q) * 0x9E3779B1u) >> (32u - BB);
-                    if (q < nh) atomicOr(&bits2[h >> 5], 1u << (h & 31u));
+                    const uint32_t old2 = q < nh ? atomicOr(&bits2[h >> 5], 1u << (h & 31u)) : 0xffffffffu;
+                    fresh += (uint32_t) __popc(__ballot_sync(ZWZ_FULL, !((old2 >> (h & 31u)) & 1u)));
                 }
+                if (lane == 0 && fresh) atomicAdd(&ctl->set2, fresh);
                 __syncthreads();
                 uint32_t hits = 0;
                 for (uint32_t st = wid; st < nfull * 32u; st += NW) {
@@ -284,9 +289,8 @@ ZWZ_KERNEL __launch_bounds__(MatchClass<CLS>::kThreads, MatchClass<CLS>::kCtasPe
                 if (lane == 0 && hits) atomicAdd(&ctl->coll2, hits);
                 __syncthreads();
                 const uint32_t nc = (uint32_t) __popcll((long long) cand) << 10;
-                const uint32_t nother = nh > nc ? nh - nc : 0u;
                 const uint32_t allowed = (uint32_t) (((uint64_t) nc * nc) >> (BB + 1u)) + (nc >> 6) + 48u;
-                const uint32_t allowed2 = (uint32_t) (((uint64_t) nother * nc) >> BB) + (nc >> 6) + 48u;
+                const uint32_t allowed2 = (uint32_t) (((uint64_t) ctl->set2 * nc) >> BB) + (nc >> 6) + 48u; // chance: n_c * (bits set) / m
                 if (tid == 0 && (ctl->coll > allowed || ctl->coll2 > allowed2)) {
                     ctl->skip[0] = 0;
                     ctl->skip[1] = 0;
